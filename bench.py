@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- Pointnet2Backbone forward throughput (scenes/s) on synthetic ScanNet-shaped scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): B=8 scenes per GPU, 40 000 points, xyz + height + 128-d
+multiview features, SA1-SA4 + FP1-FP2, fused MLPs.  A step = one backbone forward over one batch.
+Scenes are sharded by rank with no collective on the data path (weak scaling).
+
+One JSON line on rank 0:
+  value     whole-job scenes/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the public API with HOST (pinned) inputs: H2D of the batch and D2H
+            of fp2_features/fp2_xyz/fp2_inds inside the timed region, double-buffered
+  roofline  the dominant kernel of the step (largest share of device time), timed live with CUDA
+            events; roofline_kernels lists every kernel of the step the same way
+  cpu_baseline  the CPU oracle (oracle/) on this box's host cores, bounded sample, rank 0 only
+  reference_cuda  the reference's own CUDA kernels (oracle/_ref) + stock PyTorch modules on the
+            same GPU, when that extension is present -- the existing GPU implementation
+
+--impl reference times the reference's path on the host CPU (the reference ships no CPU kernels,
+its ops assert "CPU not supported", so this is the oracle port: same wiring in PyTorch CPU ops over
+the C restatement of its kernels, all host threads).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Pointnet2Backbone scenes/sec (40k pts)"
+UNIT = "scenes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=None, help="fp32 | bf16 (default: bf16 when built, else fp32)")
+    ap.add_argument("--batch", type=int, default=8, help="scenes per GPU per step")
+    ap.add_argument("--points", type=int, default=40000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-breakdown", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"hbm": float(p["hbm_gbs"]), "tensor_burst": float(p["bf16_tflops"]),
+                "tensor": float(p["bf16_tflops_sustained"]), "source": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm = []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's path on the host CPU (oracle port), bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import pn2_oracle as orc
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=129)).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    scenes = 2                                      # bounded sample: 2 of the step's 8 scenes
+    pc = torch.from_numpy(make_batch(scenes, args.points, 129))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        orc.backbone(pc, sd)                        # first call: page-in + thread pools
+        first = time.perf_counter() - t0
+        steps = max(1, min(args.steps, int(150.0 / max(first, 1e-3))))
+        warm = min(args.warmup, 2)
+        for _ in range(warm):
+            orc.backbone(pc, sd)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.backbone(pc, sd)
+        dt = time.perf_counter() - t0
+    value = scenes * steps / dt
+    sample = "%d scenes of %d points per step x %d steps (of the B=%d step); oracle port: PyTorch CPU wiring over " \
+             "oracle/pn2_oracle.c (OpenMP), %d torch threads" % (scenes, args.points, steps, args.batch, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Pointnet2Backbone forward, %d-point ScanNet-shaped scenes, 129 feature "
+                                   "channels, SA 2048/1024/512/256 + 2 FP (BASELINE configs[1] shape)" % args.points,
+                       "scenes_per_step": scenes, "device": "host CPU"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def kernel_breakdown(net, pc, precision, pk, reps=5):
+    """Every kernel of one step launched alone through the C ABI and timed with CUDA events on the
+    launching (current) stream; algorithmic bytes / FLOPs per launch as defined in DESIGN.md."""
+    import torch
+    from situation3d_b200 import fused
+    B, N, W = pc.shape
+    C = W - 3
+    sas = (net.sa1, net.sa2, net.sa3, net.sa4)
+    imgs = net._fused_images(pc)
+    xyz = pc[..., :3].contiguous()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=pc.device)
+
+    def timeit(fn):
+        fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()                       # 256 MB write: evicts L2 between repetitions
+            s, e = ev(), ev()
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        return statistics.median(ts) * 1e-3
+
+    rows = []
+    src_xyz, table, ld, c = xyz, pc[..., 3:], W, C
+    elt = 4 if precision == "fp32" else 2
+    feats_rows = []
+    cxyz_all = []
+    for lvl, m in enumerate(sas):
+        n_in = src_xyz.shape[1]
+        inds, cxyz = fused.fps_with_xyz(src_xyz, m.npoint)
+        t = timeit(lambda: fused.fps_with_xyz(src_xyz, m.npoint))
+        rows.append({"kernel": "fps_sa%d" % (lvl + 1), "bound": "hbm", "seconds": t,
+                     "alg_bytes": B * (12 * n_in + 16 * m.npoint), "rounds_per_s": B * (m.npoint - 1) / t / B})
+        idx = fused.ball_query(src_xyz, cxyz, m.radius, m.nsample)
+        t = timeit(lambda: fused.ball_query(src_xyz, cxyz, m.radius, m.nsample))
+        rows.append({"kernel": "ball_query_sa%d" % (lvl + 1), "bound": "hbm", "seconds": t,
+                     "alg_bytes": B * (12 * (n_in + m.npoint) + 4 * m.npoint * m.nsample)})
+        inv_r = 1.0 / m.radius
+        run = lambda: fused.SA_FORWARD[precision](imgs[lvl], src_xyz, cxyz, idx, table, ld, c, True, inv_r)
+        out, out_rows = run()
+        t = timeit(run)
+        dims = imgs[lvl].dims
+        flops = 2 * B * m.npoint * m.nsample * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        wbytes = 4 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        abytes = B * (4 * (c + 3) * min(n_in, m.npoint * m.nsample) + 4 * m.npoint * m.nsample
+                      + 2 * 4 * dims[-1] * m.npoint) + wbytes
+        rows.append({"kernel": "sa%d_fused_%s" % (lvl + 1, precision), "bound": "tensor", "seconds": t,
+                     "alg_flops": flops, "alg_bytes": abytes})
+        feats_rows.append(out_rows)
+        cxyz_all.append(cxyz)
+        src_xyz, table, ld, c = cxyz, out_rows, out_rows.shape[2], out_rows.shape[2]
+    known_rows = feats_rows[3]
+    for name, (u, k), skip in (("fp1", (2, 3), feats_rows[2]), ("fp2", (1, 2), feats_rows[1])):
+        un, kn = cxyz_all[u], cxyz_all[k]
+        d2, i3 = fused.three_nn(un, kn)
+        t = timeit(lambda: fused.three_nn(un, kn))
+        rows.append({"kernel": "three_nn_" + name, "bound": "hbm", "seconds": t,
+                     "alg_bytes": B * (12 * (un.shape[1] + kn.shape[1]) + 24 * un.shape[1])})
+        img = imgs[4 if name == "fp1" else 5]
+        run = lambda: fused.FP_FORWARD[precision](img, d2, i3, known_rows, skip)
+        _, out_rows = run()
+        t = timeit(run)
+        dims = img.dims
+        n = un.shape[1]
+        flops = 2 * B * n * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        abytes = B * (4 * known_rows.shape[2] * kn.shape[1] + 4 * skip.shape[2] * n + 24 * n + 2 * 4 * dims[-1] * n) \
+            + 4 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        rows.append({"kernel": "%s_fused_%s" % (name, precision), "bound": "tensor", "seconds": t,
+                     "alg_flops": flops, "alg_bytes": abytes})
+        known_rows = out_rows
+    total = sum(r["seconds"] for r in rows)
+    for r in rows:
+        r["share"] = r["seconds"] / total
+        if r["bound"] == "tensor":
+            r["achieved"], r["unit"], r["peak"] = r["alg_flops"] / r["seconds"] / 1e12, "TFLOP/s", pk["tensor_burst"]
+            r["hbm_gbs"] = r["alg_bytes"] / r["seconds"] / 1e9
+        else:
+            r["achieved"], r["unit"], r["peak"] = r["alg_bytes"] / r["seconds"] / 1e9, "GB/s", pk["hbm"]
+        r["frac"] = r["achieved"] / r["peak"]
+        r["us"] = r.pop("seconds") * 1e6
+    return rows
+
+
+def reference_cuda_arm(pc, sd, steps=3):
+    """The reference's own CUDA kernels (oracle/_ref, unmodified sources) wired as its Python modules
+    wire them (oracle restatement) with stock PyTorch conv/BN/ReLU/max-pool on the same GPU."""
+    import torch
+    from oracle import pn2_oracle as orc
+    from oracle.build_ref import load_ref_ext
+    ext = load_ref_ext()
+    if ext is None:
+        return None
+    sd = {k: v.to(pc.device) for k, v in sd.items()}
+    with torch.no_grad():
+        orc.backbone(pc, sd, ops=ext)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            orc.backbone(pc, sd, ops=ext)
+        e.record()
+        e.synchronize()
+    dt = s.elapsed_time(e) * 1e-3
+    return {"value": pc.shape[0] * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps, "steps": steps,
+            "what": "reference _ext_src kernels compiled unmodified for sm_100 + stock torch 1x1 conv/BN/ReLU/"
+                    "max_pool2d (cuDNN), fp32 (TF32 conv default), B=%d, 1 GPU" % pc.shape[0]}
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from situation3d_b200 import fused
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision or ("bf16" if "bf16" in fused.SA_FORWARD else "fp32")
+    pk = peaks()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=129, precision=precision)).eval().to(dev)
+    sd_cpu = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    # this rank's scenes: global scene ids rank*B .. rank*B+B-1 (sharded by scene, no collective)
+    host = torch.from_numpy(make_batch(B, args.points, 129, first_seed=rank * B))
+    host_pool = [host.pin_memory(), host.roll(1, 0).contiguous().pin_memory()]
+    pool = [h.to(dev) for h in host_pool]                    # each batch 169 MB > 126 MB L2
+    in_bytes = host.numel() * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        # ---- device-resident throughput -----------------------------------------------------
+        for i in range(W):
+            net({"point_clouds": pool[i % 2]})
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(K):
+            out = net({"point_clouds": pool[i % 2]})
+        e.record()
+        torch.cuda.synchronize()
+        dt = reduce_max(s.elapsed_time(e) * 1e-3)
+        barrier()
+
+        # ---- end to end: pinned host input -> H2D -> forward -> D2H of the result, double-buffered ----
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        dbuf = [torch.empty_like(pool[0]) for _ in range(2)]
+        res_host = [{k: torch.empty_like(out[k], device="cpu").pin_memory() for k in ("fp2_features", "fp2_xyz", "fp2_inds")}
+                    for _ in range(2)]
+        out_bytes = sum(v.numel() * v.element_size() for v in res_host[0].values())
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_loop(steps):
+            for i in range(steps):
+                b = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[b])          # the forward that last read dbuf[b] is done
+                    dbuf[b].copy_(host_pool[b], non_blocking=True)
+                    h2d_done[b].record(copy_stream)
+                main.wait_event(h2d_done[b])
+                o = net({"point_clouds": dbuf[b]})
+                consumed[b].record(main)
+                for k, v in res_host[b].items():
+                    v.copy_(o[k], non_blocking=True)
+
+        for ev_ in consumed:
+            ev_.record(main)
+        e2e_loop(W)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        copy_stream.wait_event(s2)
+        e2e_loop(K)
+        main.wait_stream(copy_stream)
+        e2.record()
+        torch.cuda.synchronize()
+        dt_e2e = reduce_max(s2.elapsed_time(e2) * 1e-3)
+        clocks = sampler.stop() if sampler else None
+        barrier()
+
+        rows, ref_cuda, cpu_base = None, None, None
+        if rank == 0:
+            if not args.no_kernel_breakdown:
+                rows = kernel_breakdown(net, pool[0], precision, pk)
+            try:
+                ref_cuda = reference_cuda_arm(pool[0], sd_cpu)
+            except Exception as ex:   # test infrastructure must not take the bench down
+                ref_cuda = {"unavailable": repr(ex)[:200]}
+            if not args.no_cpu_baseline:
+                from oracle import pn2_oracle as orc
+                cores = os.cpu_count() or 1
+                torch.set_num_threads(cores)
+                sample = host[: min(B, 4)].contiguous()
+                orc.backbone(sample[:1].contiguous(), sd_cpu)
+                t0 = time.perf_counter()
+                orc.backbone(sample, sd_cpu)
+                t1 = time.perf_counter() - t0
+                cpu_base = {"value": sample.shape[0] / t1, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "%d of the step's %d scenes, one pass after a 1-scene warm-up; oracle port "
+                                      "(PyTorch CPU wiring over oracle/pn2_oracle.c, OpenMP + %d torch threads)"
+                                      % (sample.shape[0], B, cores)}
+        barrier()
+
+    if rank == 0:
+        launches_per_step = 4 + 4 + 4 + 2 + 2          # fps, ball query, fused SA, three_nn, fused FP
+        line = {"metric": METRIC, "value": world * B * K / dt, "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": "Pointnet2Backbone forward (SA1-SA4 + FP1-FP2), B=%d scenes/GPU x %d points, "
+                                       "xyz+height+128-d multiview (BASELINE configs[1])" % (B, args.points),
+                           "scenes_per_gpu": B, "points": args.points, "feature_channels": 129,
+                           "precision": precision, "sharding": "by scene, no collective",
+                           "l2": "each input batch is %.0f MB (> 126 MB L2); two batches alternate" % (in_bytes / 1e6)},
+                "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "ms_per_step": 1e3 * dt_e2e / K,
+                        "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                        "api": "Pointnet2Backbone.forward(data_dict) on pinned host point_clouds"},
+                "gpu_launches": launches_per_step * K, "clocks": clocks, "peaks": pk}
+        if rows:
+            dom = max(rows, key=lambda r: r["share"])
+            line["roofline"] = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
+                                "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
+                                "share_of_step": dom["share"], "us_per_launch": dom["us"],
+                                "peak_source": pk["source"] + (" burst" if dom["bound"] == "tensor" else "")}
+            if "rounds_per_s" in dom:
+                line["roofline"]["rounds_per_s"] = dom["rounds_per_s"]
+            line["roofline_kernels"] = [
+                {k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()
+                 if k in ("kernel", "bound", "us", "share", "achieved", "unit", "frac", "hbm_gbs", "rounds_per_s")}
+                for r in rows]
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        if ref_cuda:
+            line["reference_cuda"] = ref_cuda
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517")] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
 
 #define PN2_OK 0
 #define PN2_ERR_INVALID_ARGUMENT (-1)   /* bad dims / null pointer / unsupported shape */
@@ -105,60 +108,60 @@ int pn2_group_points(int b, int c, int n, int npoints, int nsample, const float 
 int pn2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
                           const int *idx, float *grad_points, pn2_stream_t stream);
 
-/* ---- fused set-abstraction layer --------------------------------------
- * Replaces, for eval-mode PointnetSAModuleVotes(use_xyz=True, pooling='max'), the chain
- *   QueryAndGroup.forward           pointnet2_utils.py:348-359 (group xyz, recentre, /radius, group feats, cat)
- *   SharedMLP (3x Conv2d 1x1 + BN + ReLU)   pytorch_utils.py:11-36,67-121
- *   F.max_pool2d over nsample       pointnet2_modules.py:259-262
- * given the ball-query indices.  BatchNorm is folded into the weights by the caller
- * (SURVEY.md A.5); the MLP runs on tcgen05 tensor cores with bf16 operands and fp32
- * accumulation in TMEM.
+/* Same as pn2_furthest_point_sampling, and also writes the sampled coordinates
+ * new_xyz (b,m,3) = xyz[idxs] (may be NULL).  Fuses the gather_operation + two transposes
+ * of PointnetSAModuleVotes.forward (pointnet2_modules.py:233-240) into the sampling kernel:
+ * every CTA already holds the winner's coordinates each round. */
+int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *idxs,
+                                    float *new_xyz, pn2_stream_t stream);
+
+/* ---- fused SharedMLP layers, full precision ------------------------------
+ * A SharedMLP (pytorch_utils.py:11-36: 1x1 Conv2d without bias -> BatchNorm2d -> ReLU per
+ * layer) in eval mode is described by `nlayers` and host array dims[nlayers+1]
+ * (dims[0] = input width) plus, per layer, the BatchNorm-folded weight (cout,cin) row-major
+ * and bias (cout).  pn2_mlp_f32_pack turns them into one device image
+ * (transposed, padded) of pn2_mlp_f32_image_bytes() bytes that the fused kernels consume.
+ * w / bias are HOST arrays of nlayers DEVICE pointers; bias or bias[l] may be NULL (zeros).
+ * At most 4 layers; pn2_mlp_f32_supported() says whether the widths fit shared memory.
  */
+size_t pn2_mlp_f32_image_bytes(int nlayers, const int *dims);
+int pn2_mlp_f32_supported(int nlayers, const int *dims);
+int pn2_mlp_f32_pack(int nlayers, const int *dims, const float *const *w, const float *const *bias,
+                     void *image, pn2_stream_t stream);
 
-/* Pack (b,c,n) f32 channel-first features into the channel-last bf16 row table the fused
- * kernel gathers from: table (b, n, row_elems) bf16, row = [feat_0..feat_{c-1}, 0 ...].
- * row_elems = pn2_sa_row_elems(c).  features may be NULL when c == 0. */
-int pn2_sa_row_elems(int c);
-int pn2_sa_pack_features(int b, int c, int n, const float *features, void *table,
-                         pn2_stream_t stream);
-/* Same, from a channel-last f32 source with row stride `src_stride` floats whose first
- * `skip` floats are not features (the backbone's point_clouds (b,n,3+c) input). */
-int pn2_sa_pack_features_cl(int b, int c, int n, const float *src, int src_stride, int skip,
-                            void *table, pn2_stream_t stream);
+/* (b,c,n) channel-first -> (b,n,c) channel-last rows: the layout the fused kernels gather
+ * from (one contiguous row per point instead of the reference's stride-N reads,
+ * group_points_gpu.cu:23-26). */
+int pn2_rows_from_channels(int b, int c, int n, const float *src, float *dst, pn2_stream_t stream);
 
-/* Folded weights -> device image consumed by pn2_sa_forward.
- *   w1 (c1, 3+c) f32 row-major with the reference channel order [dx,dy,dz,feat...],
- *   w2 (c2, c1), w3 (c3, c2); b1,b2,b3 folded biases.  image: pn2_sa_weight_image_bytes(). */
-size_t pn2_sa_weight_image_bytes(int c, int c1, int c2, int c3);
-int pn2_sa_pack_weights(int c, int c1, int c2, int c3, const float *w1, const float *b1,
-                        const float *w2, const float *b2, const float *w3, const float *b3,
-                        void *image, pn2_stream_t stream);
-
-/* xyz (b,n,3) f32, new_xyz (b,npoint,3) f32, table from pn2_sa_pack_features, idx
- * (b,npoint,nsample) i32 -> out (b,c3,npoint) f32 and, if out_table != NULL, the same values
- * as the next layer's bf16 row table (b,npoint,pn2_sa_row_elems(c3)).
- * inv_radius = 1/radius when normalize_xyz, else 1.  Returns PN2_ERR_INVALID_ARGUMENT for
- * shapes outside pn2_sa_supported(). */
-int pn2_sa_supported(int c, int c1, int c2, int c3, int nsample);
-int pn2_sa_forward(int b, int n, int npoint, int nsample, int c, int c1, int c2, int c3,
-                   float inv_radius, const float *xyz, const float *new_xyz, const void *table,
-                   const int *idx, const void *weight_image, float *out, void *out_table,
-                   pn2_stream_t stream);
-
-/* ---- fused feature-propagation layer ----------------------------------
- * Replaces PointnetFPModule.forward (pointnet2_modules.py:399-421) for eval mode:
- * three_nn -> 1/(d+1e-8) weights -> three_interpolate -> cat(skip) -> SharedMLP (2 layers).
+/* Fused set-abstraction layer, fp32.  Replaces, for eval-mode
+ * PointnetSAModuleVotes(pooling='max'), the chain
+ *   QueryAndGroup.forward   pointnet2_utils.py:348-359 (group xyz, recentre, /radius, group feats, cat)
+ *   SharedMLP               pytorch_utils.py:11-36,67-121
+ *   F.max_pool2d            pointnet2_modules.py:259-262
+ * given the ball-query indices idx (b,npoint,nsample).
+ *   table: channel-last feature rows, row (s,p) at table + (s*n + p)*ld, first c floats used
+ *          (for the backbone input point_clouds (b,n,3+c): table = pc + 3, ld = 3 + c);
+ *   use_xyz: prepend (xyz[idx] - new_xyz) * inv_radius (inv_radius = 1/radius when
+ *          normalize_xyz, else 1); dims[0] must equal c + 3*use_xyz;
+ *   out (b,cout,npoint) f32; out_rows (b,npoint,cout) f32 or NULL (next layer's table).
  */
-size_t pn2_fp_weight_image_bytes(int c_in, int c1, int c2);
-int pn2_fp_pack_weights(int c_in, int c1, int c2, const float *w1, const float *b1,
-                        const float *w2, const float *b2, void *image, pn2_stream_t stream);
-int pn2_fp_supported(int c_known, int c_skip, int c1, int c2);
-/* unknown (b,n,3), known (b,m,3), known_feats (b,c_known,m) f32, skip_feats (b,c_skip,n) f32
- * -> out (b,c2,n) f32.  dist2/idx (b,n,3) from pn2_three_nn. */
-int pn2_fp_forward(int b, int n, int m, int c_known, int c_skip, int c1, int c2,
-                   const float *dist2, const int *idx, const float *known_feats,
-                   const float *skip_feats, const void *weight_image, float *out,
-                   pn2_stream_t stream);
+int pn2_sa_forward_f32(int b, int n, int npoint, int nsample, int c, const float *table, int ld,
+                       int use_xyz, float inv_radius, const float *xyz, const float *new_xyz,
+                       const int *idx, int nlayers, const int *dims, const void *image, float *out,
+                       float *out_rows, pn2_stream_t stream);
+
+/* Fused feature-propagation layer, fp32.  Replaces PointnetFPModule.forward
+ * (pointnet2_modules.py:399-421) in eval mode after three_nn: sqrt -> 1/(d+1e-8) ->
+ * normalise -> three_interpolate -> cat(skip) -> SharedMLP.
+ *   dist2, idx (b,n,3) from pn2_three_nn; known_rows (b,m,c_known), skip_rows (b,n,c_skip)
+ *   channel-last (skip_rows may be NULL when c_skip == 0); dims[0] = c_known + c_skip;
+ *   out (b,cout,n); out_rows (b,n,cout) or NULL.
+ */
+int pn2_fp_forward_f32(int b, int n, int m, int c_known, int c_skip, const float *dist2,
+                       const int *idx, const float *known_rows, const float *skip_rows, int nlayers,
+                       const int *dims, const void *image, float *out, float *out_rows,
+                       pn2_stream_t stream);
 
 /* ---- situation-conditioned re-encoding --------------------------------
  * tokens (b,t,d) f32, positions (b,t,3) f32, situation (b,7) f32 = (tx,ty,tz,qx,qy,qz,qw).
@@ -173,6 +176,16 @@ int pn2_reencode_forward(int b, int t, int d, int h, int mode, float sigma, cons
                          const float *b1, const float *w2, const float *b2, float *out,
                          float *new_pos, float *prior, pn2_stream_t stream);
 
+/* quats (b,4) xyzw -> (b,3,3): quaternions_to_rotation_matrices, sqa_module.py:12-30 */
+int pn2_quaternions_to_rotation_matrices(int b, const float *quats, float *out, pn2_stream_t stream);
+/* rotvecs (b,3) -> (b,3,3): batch_rotation_vector_to_matrix, sqa_module.py:33-64 */
+int pn2_rotation_vectors_to_matrices(int b, const float *rotvecs, float *out, pn2_stream_t stream);
+/* situation (b,7) -> (b,4,4): batch_matrix_function, situation3d/utils/temp.py:42-80 */
+int pn2_situation_matrices(int b, const float *situation, float *out, pn2_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

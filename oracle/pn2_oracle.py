@@ -1,0 +1,307 @@
+"""Python face of the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this file; nothing under situation3d_b200/ does.  It is the checker (and the timed CPU
+baseline), never the product path.
+
+Two layers:
+  * the nine lib/pointnet2 operators, executed by oracle/pn2_oracle.c (a C restatement of the
+    reference CUDA kernels with their exact fmaf order; built by oracle/Makefile);
+  * the module wiring restated with plain PyTorch CPU ops, each function citing the reference
+    lines it follows: QueryAndGroup, SharedMLP (eval), PointnetSAModuleVotes,
+    PointnetFPModule, the Pointnet2Backbone composition driven directly by a
+    state_dict with the reference's key names, and the situation re-encoding.
+
+Parity pinning: the operators are pinned against the reference's own CUDA extension
+(oracle/_ref, built unmodified from /root/reference by oracle/build_ref.py and run on the GPU
+box; vectors in tests/golden/ref_cuda_ops.npz), the wiring against the reference's own Python
+modules imported from /root/reference (tests/golden/ref_modules.npz, made by
+tests/golden/make_ref_module_goldens.py).  The 1x1 conv / BatchNorm arithmetic itself is
+third-party (PyTorch 1.12 + cuDNN 8.3 in the reference environment, environment.yml:60) and
+is compared by tolerance only.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libpn2_oracle.so")
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(
+                os.path.join(_HERE, "pn2_oracle.c")):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.pn2o_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def num_threads():
+    return int(lib().pn2o_num_threads())
+
+
+def _f32(t):
+    t = torch.as_tensor(t)
+    assert t.dtype == torch.float32 and not t.is_cuda
+    return t.contiguous()
+
+
+def _i32(t):
+    t = torch.as_tensor(t)
+    assert t.dtype == torch.int32 and not t.is_cuda
+    return t.contiguous()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+# ---- the nine operators (same names / argument order as pointnet2._ext) ------------------
+
+def furthest_point_sampling(points, nsamples):
+    points = _f32(points)
+    B, N, _ = points.shape
+    out = torch.zeros((B, nsamples), dtype=torch.int32)
+    lib().pn2o_furthest_point_sampling(B, N, int(nsamples), _p(points), _p(out))
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    new_xyz, xyz = _f32(new_xyz), _f32(xyz)
+    B, m, _ = new_xyz.shape
+    out = torch.zeros((B, m, nsample), dtype=torch.int32)
+    lib().pn2o_ball_query(B, xyz.shape[1], m, ctypes.c_float(radius), int(nsample), _p(new_xyz), _p(xyz), _p(out))
+    return out
+
+
+def three_nn(unknowns, knows):
+    unknowns, knows = _f32(unknowns), _f32(knows)
+    B, n, _ = unknowns.shape
+    dist2 = torch.zeros((B, n, 3), dtype=torch.float32)
+    idx = torch.zeros((B, n, 3), dtype=torch.int32)
+    lib().pn2o_three_nn(B, n, knows.shape[1], _p(unknowns), _p(knows), _p(dist2), _p(idx))
+    return [dist2, idx]
+
+
+def three_interpolate(points, idx, weight):
+    points, idx, weight = _f32(points), _i32(idx), _f32(weight)
+    B, c, m = points.shape
+    n = idx.shape[1]
+    out = torch.zeros((B, c, n), dtype=torch.float32)
+    lib().pn2o_three_interpolate(B, c, m, n, _p(points), _p(idx), _p(weight), _p(out))
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    grad_out, idx, weight = _f32(grad_out), _i32(idx), _f32(weight)
+    B, c, n = grad_out.shape
+    out = torch.zeros((B, c, m), dtype=torch.float32)
+    lib().pn2o_three_interpolate_grad(B, c, n, int(m), _p(grad_out), _p(idx), _p(weight), _p(out))
+    return out
+
+
+def gather_points(points, idx):
+    points, idx = _f32(points), _i32(idx)
+    B, C, N = points.shape
+    m = idx.shape[1]
+    out = torch.zeros((B, C, m), dtype=torch.float32)
+    lib().pn2o_gather_points(B, C, N, m, _p(points), _p(idx), _p(out))
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    grad_out, idx = _f32(grad_out), _i32(idx)
+    B, C, m = grad_out.shape
+    out = torch.zeros((B, C, n), dtype=torch.float32)
+    lib().pn2o_gather_points_grad(B, C, int(n), m, _p(grad_out), _p(idx), _p(out))
+    return out
+
+
+def group_points(points, idx):
+    points, idx = _f32(points), _i32(idx)
+    B, C, N = points.shape
+    _, npoints, nsample = idx.shape
+    out = torch.zeros((B, C, npoints, nsample), dtype=torch.float32)
+    lib().pn2o_group_points(B, C, N, npoints, nsample, _p(points), _p(idx), _p(out))
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    grad_out, idx = _f32(grad_out), _i32(idx)
+    B, C, npoints, nsample = grad_out.shape
+    out = torch.zeros((B, C, n), dtype=torch.float32)
+    lib().pn2o_group_points_grad(B, C, int(n), npoints, nsample, _p(grad_out), _p(idx), _p(out))
+    return out
+
+
+# ---- module wiring restated with PyTorch CPU ops ---------------------------------------
+
+class _CpuOps:
+    """The C restatement above.  ``ops=`` lets bench.py run the SAME wiring over the reference's own
+    CUDA extension (oracle/_ref) with CUDA tensors: that is the reference's stock GPU path."""
+    furthest_point_sampling = staticmethod(furthest_point_sampling)
+    ball_query = staticmethod(ball_query)
+    three_nn = staticmethod(three_nn)
+    three_interpolate = staticmethod(three_interpolate)
+    gather_points = staticmethod(gather_points)
+    group_points = staticmethod(group_points)
+
+
+def query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, normalize_xyz=False, ops=_CpuOps):
+    """pointnet2_utils.py:317-376 (sample_uniformly off).  Returns (new_features, grouped_xyz, idx)."""
+    ball_query, group_points = ops.ball_query, ops.group_points
+    idx = ball_query(new_xyz, xyz, radius, nsample)                       # :334
+    grouped_xyz = group_points(xyz.transpose(1, 2).contiguous(), idx)     # :347-348
+    grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)     # :349
+    if normalize_xyz:
+        grouped_xyz = grouped_xyz / radius                                # :350-351
+    if features is not None:
+        grouped = group_points(features, idx)                             # :354
+        new_features = torch.cat([grouped_xyz, grouped], dim=1) if use_xyz else grouped   # :355-360
+    else:
+        new_features = grouped_xyz
+    return new_features, grouped_xyz, idx
+
+
+def shared_mlp_eval(x, sd, prefix, nlayers, eps=1e-5):
+    """pytorch_utils.py:11-36,67-121 in eval mode, from state-dict tensors:
+    conv 1x1 (no bias when BN follows) -> BatchNorm2d(running stats) -> ReLU, per layer."""
+    for i in range(nlayers):
+        w = sd["%slayer%d.conv.weight" % (prefix, i)]
+        b = sd.get("%slayer%d.conv.bias" % (prefix, i))
+        x = F.conv2d(x, w, b)
+        key = "%slayer%d.bn.bn." % (prefix, i)
+        if key + "weight" in sd:
+            x = F.batch_norm(x, sd[key + "running_mean"], sd[key + "running_var"], sd[key + "weight"],
+                             sd[key + "bias"], training=False, eps=eps)
+        x = F.relu(x)
+    return x
+
+
+def _count_layers(sd, prefix):
+    n = 0
+    while "%slayer%d.conv.weight" % (prefix, n) in sd:
+        n += 1
+    return n
+
+
+def sa_module_votes(xyz, features, sd, prefix, npoint, radius, nsample, use_xyz=True, normalize_xyz=False,
+                    inds=None, ops=_CpuOps):
+    """PointnetSAModuleVotes.forward with max pooling (pointnet2_modules.py:210-277).
+    Returns (new_xyz, new_features, inds, ball_idx)."""
+    if inds is None:
+        inds = ops.furthest_point_sampling(xyz, npoint)                    # :235
+    new_xyz = ops.gather_points(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()   # :238-240
+    grouped, _, idx = query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz, normalize_xyz, ops)
+    x = shared_mlp_eval(grouped, sd, prefix + "mlp_module.", _count_layers(sd, prefix + "mlp_module."))   # :251
+    x = F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)            # :259-262,272
+    return new_xyz, x, inds, idx
+
+
+def fp_module(unknown, known, unknow_feats, known_feats, sd, prefix, ops=_CpuOps):
+    """PointnetFPModule.forward (pointnet2_modules.py:376-421)."""
+    three_interpolate = ops.three_interpolate
+    dist2, idx = ops.three_nn(unknown, known)
+    dist = torch.sqrt(dist2)                                               # pointnet2_utils.py:142
+    dist_recip = 1.0 / (dist + 1e-8)                                       # :400
+    norm = torch.sum(dist_recip, dim=2, keepdim=True)
+    weight = dist_recip / norm                                             # :401-402
+    interpolated = three_interpolate(known_feats, idx, weight)             # :404-406
+    x = torch.cat([interpolated, unknow_feats], dim=1) if unknow_feats is not None else interpolated   # :412-416
+    x = shared_mlp_eval(x.unsqueeze(-1), sd, prefix + "mlp.", _count_layers(sd, prefix + "mlp."))      # :418-419
+    return x.squeeze(-1)
+
+
+BACKBONE_LAYERS = (   # (name, npoint, radius, nsample)
+    ("sa1", 2048, 0.2, 64), ("sa2", 1024, 0.4, 32), ("sa3", 512, 0.8, 16), ("sa4", 256, 1.2, 16))
+
+
+def backbone(point_clouds, sd, layers=BACKBONE_LAYERS, ops=_CpuOps):
+    """Pointnet2Backbone.forward (composition of SURVEY.md 3.3 / 8a-0) from a state_dict with
+    the reference's key names.  Returns the same dictionary keys as the product."""
+    pc = _f32(point_clouds) if ops is _CpuOps else point_clouds
+    xyz = pc[..., 0:3].contiguous()
+    features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+    out = {}
+    for name, npoint, radius, nsample in layers:
+        xyz, features, inds, idx = sa_module_votes(xyz, features, sd, name + ".", npoint, radius, nsample,
+                                                  use_xyz=True, normalize_xyz=True, ops=ops)
+        out[name + "_xyz"], out[name + "_features"], out[name + "_inds"], out[name + "_ball_idx"] = \
+            xyz, features, inds, idx
+    f = fp_module(out["sa3_xyz"], out["sa4_xyz"], out["sa3_features"], out["sa4_features"], sd, "fp1.", ops)
+    f = fp_module(out["sa2_xyz"], out["sa3_xyz"], out["sa2_features"], f, sd, "fp2.", ops)
+    out["fp2_features"] = f
+    out["fp2_xyz"] = out["sa2_xyz"]
+    out["fp2_inds"] = out["sa1_inds"][:, 0:out["fp2_xyz"].shape[1]]
+    return out
+
+
+# ---- situation re-encoding --------------------------------------------------------------
+
+def quaternions_to_rotation_matrices(q):
+    """sqa_module.py:12-30 (xyzw, not normalised)."""
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.zeros((q.shape[0], 3, 3), dtype=q.dtype)
+    R[:, 0, 0] = 1 - 2 * (y ** 2 + z ** 2); R[:, 0, 1] = 2 * (x * y - z * w); R[:, 0, 2] = 2 * (x * z + y * w)
+    R[:, 1, 0] = 2 * (x * y + z * w); R[:, 1, 1] = 1 - 2 * (x ** 2 + z ** 2); R[:, 1, 2] = 2 * (y * z - x * w)
+    R[:, 2, 0] = 2 * (x * z - y * w); R[:, 2, 1] = 2 * (y * z + x * w); R[:, 2, 2] = 1 - 2 * (x ** 2 + y ** 2)
+    return R
+
+
+def batch_rotation_vector_to_matrix(v):
+    """sqa_module.py:33-64: Rodrigues, identity rows where |v| < 1e-6."""
+    theta = torch.norm(v, dim=1, keepdim=True)
+    eye = torch.eye(3).repeat(v.shape[0], 1, 1)
+    small = theta < 1e-6
+    if small.all():
+        return eye
+    u = v / theta
+    zeros = torch.zeros(v.shape[0], 1)
+    K = torch.cat([torch.cat([zeros, -u[:, 2:3], u[:, 1:2]], dim=1),
+                   torch.cat([u[:, 2:3], zeros, -u[:, 0:1]], dim=1),
+                   torch.cat([-u[:, 1:2], u[:, 0:1], zeros], dim=1)], dim=1).view(-1, 3, 3)
+    th = theta.view(-1, 1, 1)
+    R = eye + torch.sin(th) * K + (1 - torch.cos(th)) * torch.matmul(K, K)
+    R[small.squeeze(1)] = eye[small.squeeze(1)]
+    return R
+
+
+def batch_matrix_function(s):
+    """situation3d/utils/temp.py:42-80: (B,7) -> (B,4,4)."""
+    x, y, z, w = s[:, 3], s[:, 4], s[:, 5], s[:, 6]
+    M = torch.zeros((s.shape[0], 4, 4), dtype=s.dtype)
+    M[:, 0, 0] = x * x - y * y - z * z + w * w; M[:, 0, 1] = 2 * (x * y - z * w); M[:, 0, 2] = 2 * (x * z + y * w)
+    M[:, 1, 0] = 2 * (x * y + z * w); M[:, 1, 1] = -x * x + y * y - z * z + w * w; M[:, 1, 2] = 2 * (y * z - x * w)
+    M[:, 2, 0] = 2 * (x * z - y * w); M[:, 2, 1] = 2 * (y * z + x * w); M[:, 2, 2] = -x * x - y * y + z * z + w * w
+    M[:, 0, 3], M[:, 1, 3], M[:, 2, 3], M[:, 3, 3] = s[:, 0], s[:, 1], s[:, 2], 1
+    return M
+
+
+def reencode(tokens, positions, situation, w1, b1, w2, b2, to_agent_frame=False, sigma=0.16):
+    """temp.py:86-97 transform, sqa_module.py:274-278,319-321 embedding + add, :328-336 prior."""
+    M = batch_matrix_function(situation)
+    if to_agent_frame:
+        R, t = M[:, :3, :3], M[:, :3, 3]
+        new_pos = torch.bmm(positions - t[:, None, :], R)          # rows: R^T (p - t)
+    else:
+        aug = torch.cat([positions, torch.ones_like(positions[..., :1])], dim=2)
+        new_pos = torch.bmm(aug, M.transpose(1, 2))[:, :, :3]
+    pe = F.linear(F.gelu(F.linear(new_pos[..., :2], w1, b1)), w2, b2)
+    out = tokens + pe
+    dist = torch.norm(positions[..., :2] - situation[:, None, :2], dim=2)
+    wgt = torch.exp(-dist ** 2 / (2 * sigma ** 2))
+    prior = wgt / wgt.sum(dim=1, keepdim=True)
+    return out, new_pos, prior

@@ -1,0 +1,143 @@
+"""Pointnet2Backbone: SA1-SA4 + FP1-FP2 over the drop-in pointnet2 modules.
+
+The class is absent from /root/reference; the composition is the upstream
+VoteNet / ScanQA ``models/backbone_module.py`` that SIG3D's loss helpers still expect
+(``lib/loss_helper.py:47-59`` reads ``fp2_xyz``/``fp2_features``/``fp2_inds`` as seeds), with
+the layer table of SURVEY.md 8a-0 (corroborated by the shape comment at
+``lib/pointnet2/pointnet2_modules.py:253-255``).
+
+Eval-mode forward on CUDA is the fused B200 path:
+  * the sampling pyramid (the four furthest-point chains, each fed by the previous level's
+    sampled coordinates) depends on xyz only and runs ahead on its own stream;
+  * per level, on the main stream: ball query -> one fused gather + MLP + max-pool kernel that
+    reads channel-last rows (for SA1 straight out of ``point_clouds``) and writes both the
+    reference's (B,C,npoint) tensor and the channel-last rows the next level gathers from;
+  * FP1/FP2: three_nn -> one fused interpolate + concat + MLP kernel.
+Training mode (or fused=False) runs the same modules operator by operator with autograd.
+"""
+import torch
+import torch.nn as nn
+
+from . import fused as _fused
+from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+
+
+class Pointnet2Backbone(nn.Module):
+    r"""
+    Parameters
+    ----------
+    input_feature_dim : int
+        Channels per point besides xyz (129 for SIG3D/ScanQA: height + 128-d multiview).
+    precision : "fp32" | "bf16"
+        Arithmetic of the fused shared MLPs.
+    """
+
+    def __init__(self, input_feature_dim=0, *, precision="fp32", fused=True,
+                 npoints=(2048, 1024, 512, 256), radii=(0.2, 0.4, 0.8, 1.2), nsamples=(64, 32, 16, 16)):
+        super().__init__()
+        self.input_feature_dim = input_feature_dim
+        self.precision = precision
+        self.fused = fused
+        kw = dict(use_xyz=True, normalize_xyz=True, fused=fused, precision=precision)
+        self.sa1 = PointnetSAModuleVotes(npoint=npoints[0], radius=radii[0], nsample=nsamples[0],
+                                         mlp=[input_feature_dim, 64, 64, 128], **kw)
+        self.sa2 = PointnetSAModuleVotes(npoint=npoints[1], radius=radii[1], nsample=nsamples[1],
+                                         mlp=[128, 128, 128, 256], **kw)
+        self.sa3 = PointnetSAModuleVotes(npoint=npoints[2], radius=radii[2], nsample=nsamples[2],
+                                         mlp=[256, 128, 128, 256], **kw)
+        self.sa4 = PointnetSAModuleVotes(npoint=npoints[3], radius=radii[3], nsample=nsamples[3],
+                                         mlp=[256, 128, 128, 256], **kw)
+        self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
+        self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
+        self._side_stream = None
+
+    @staticmethod
+    def _break_up_pc(pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def set_precision(self, precision):
+        self.precision = precision
+        for m in (self.sa1, self.sa2, self.sa3, self.sa4, self.fp1, self.fp2):
+            m.precision = precision
+
+    # ---- fused eval path -------------------------------------------------------------------
+    def _fused_images(self, pc):
+        if not (self.fused and pc.is_cuda and pc.dtype == torch.float32 and pc.size(-1) > 3):
+            return None
+        sas = (self.sa1, self.sa2, self.sa3, self.sa4)
+        imgs = [m._fused_image(pc) for m in sas] + [m._fused_image(pc) for m in (self.fp1, self.fp2)]
+        return None if any(i is None for i in imgs) else imgs
+
+    def _forward_fused(self, pc, imgs, data_dict):
+        B, N, W = pc.shape
+        pc = pc.contiguous()
+        dev = pc.device
+        sas = (self.sa1, self.sa2, self.sa3, self.sa4)
+        xyz = pc[..., 0:3].contiguous()
+        main = torch.cuda.current_stream(dev)
+        if self._side_stream is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        side = self._side_stream
+
+        # buffers are allocated on the main stream; the side stream only fills them
+        inds = [torch.empty((B, m.npoint), dtype=torch.int32, device=dev) for m in sas]
+        cxyz = [torch.empty((B, m.npoint, 3), dtype=torch.float32, device=dev) for m in sas]
+        ready = [torch.cuda.Event() for _ in sas]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            src = xyz
+            for lvl, m in enumerate(sas):
+                _fused.fps_into(src, inds[lvl], cxyz[lvl])
+                ready[lvl].record(side)
+                src = cxyz[lvl]
+
+        feats, rows = [], []
+        src_xyz, table, ld, c = xyz, pc[..., 3:], W, W - 3
+        for lvl, m in enumerate(sas):
+            main.wait_event(ready[lvl])
+            idx = _fused.ball_query(src_xyz, cxyz[lvl], m.radius, m.nsample)
+            inv_r = 1.0 / m.radius if m.normalize_xyz else 1.0
+            out, out_rows = _fused.SA_FORWARD[self.precision](imgs[lvl], src_xyz, cxyz[lvl], idx, table, ld, c,
+                                                             m.use_xyz, inv_r)
+            feats.append(out)
+            rows.append(out_rows)
+            src_xyz, table, ld, c = cxyz[lvl], out_rows, out_rows.shape[2], out_rows.shape[2]
+            data_dict["sa%d_inds" % (lvl + 1)] = inds[lvl]
+            data_dict["sa%d_xyz" % (lvl + 1)] = cxyz[lvl]
+            data_dict["sa%d_features" % (lvl + 1)] = out
+
+        d2, i3 = _fused.three_nn(cxyz[2], cxyz[3])
+        _, fp1_rows = _fused.FP_FORWARD[self.precision](imgs[4], d2, i3, rows[3], rows[2])
+        d2, i3 = _fused.three_nn(cxyz[1], cxyz[2])
+        fp2, _ = _fused.FP_FORWARD[self.precision](imgs[5], d2, i3, fp1_rows, rows[1], want_rows=False)
+        data_dict["fp2_features"] = fp2
+        data_dict["fp2_xyz"] = cxyz[1]
+        data_dict["fp2_inds"] = inds[0][:, 0:cxyz[1].shape[1]]
+        return data_dict
+
+    def forward(self, data_dict):
+        r"""Reads ``data_dict["point_clouds"]`` (B, N, 3 + input_feature_dim) and adds
+        ``sa{1..4}_{xyz,features,inds}``, ``fp2_features`` (B,256,1024), ``fp2_xyz``, ``fp2_inds``."""
+        pc = data_dict["point_clouds"]
+        if not self.training and not (torch.is_grad_enabled() and pc.requires_grad):
+            imgs = self._fused_images(pc)
+            if imgs is not None:
+                return self._forward_fused(pc, imgs, data_dict)
+
+        xyz, features = self._break_up_pc(pc)
+        for lvl, m in enumerate((self.sa1, self.sa2, self.sa3, self.sa4), start=1):
+            xyz, features, fps_inds = m(xyz, features)
+            data_dict["sa%d_inds" % lvl] = fps_inds
+            data_dict["sa%d_xyz" % lvl] = xyz
+            data_dict["sa%d_features" % lvl] = features
+
+        features = self.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"], data_dict["sa3_features"],
+                            data_dict["sa4_features"])
+        features = self.fp2(data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], features)
+        data_dict["fp2_features"] = features
+        data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
+        num_seed = data_dict["fp2_xyz"].shape[1]
+        data_dict["fp2_inds"] = data_dict["sa1_inds"][:, 0:num_seed]
+        return data_dict

@@ -37,7 +37,7 @@ void set_cuda_error(cudaError_t e, const char *where);
 
 static inline cudaStream_t as_stream(pn2_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- the one distance recipe every index-producing kernel shares ----------
 // nvcc contracts the reference's (a-b)*(a-b) + (c-d)*(c-d) + (e-f)*(e-f) into

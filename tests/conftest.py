@@ -1,0 +1,42 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def ref_modules_golden(golden_dir):
+    import numpy as np
+    return dict(np.load(os.path.join(golden_dir, "ref_modules.npz")))
+
+
+@pytest.fixture(scope="session")
+def ref_cuda_golden(golden_dir):
+    import numpy as np
+    path = os.path.join(golden_dir, "ref_cuda_ops.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_cuda_ops.npz not generated yet (needs the GPU box)")
+    return dict(np.load(path))

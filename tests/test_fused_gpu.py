@@ -1,0 +1,269 @@
+"""GPU parity suite, part 2: the SA / FP modules, the backbone and the situation re-encoding
+through the reference-facing Python API, against the CPU oracle's restatement of the reference
+wiring and the golden vectors produced by the reference's own Python modules.
+
+Tolerances (BASELINE.json north_star): indices bit-exact; features rtol 1e-3 for fp32,
+2e-2 for bf16 (relative to the tensor's scale, see ``assert_features``)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pn2_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {"fp32": 1e-3, "bf16": 2e-2}
+
+
+def assert_features(got, want, precision):
+    """|got - want| <= rtol * max(|want|, rms(want)): element-wise relative error with the usual
+    floor for entries that cancel to ~0 (post-ReLU features are exactly 0 in many places)."""
+    got, want = got.float().cpu(), want.float().cpu()
+    assert got.shape == want.shape
+    floor = want.pow(2).mean().sqrt()
+    err = (got - want).abs()
+    bound = RTOL[precision] * torch.maximum(want.abs(), floor)
+    assert bool((err <= bound).all()), "max err %.3e (bound %.3e) at scale %.3e" % (
+        float(err.max()), float(bound.flatten()[err.argmax()]), float(floor))
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def precisions():
+    from situation3d_b200 import fused
+    return sorted(fused.SA_FORWARD.keys())
+
+
+# ---- golden vectors made by the reference's Python modules ----------------------------------------
+
+@pytest.mark.parametrize("name,kw", [
+    ("sa_a", dict(npoint=32, radius=0.6, nsample=16, mlp=[6, 16, 16, 32], normalize_xyz=True)),
+    ("sa_b", dict(npoint=20, radius=0.9, nsample=8, mlp=[6, 24, 40], normalize_xyz=False)),
+    ("sa_c", dict(npoint=16, radius=0.7, nsample=80, mlp=[6, 16, 32], normalize_xyz=True))])
+@pytest.mark.parametrize("fused", [True, False])
+def test_sa_module_vs_reference_python_golden(ref_modules_golden, name, kw, fused):
+    from situation3d_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
+    g = ref_modules_golden
+    mod = PointnetSAModuleVotes(fused=fused, precision="fp32", **{k: (list(v) if isinstance(v, list) else v)
+                                                                 for k, v in kw.items()})
+    mod.load_state_dict({k[len(name) + 4:]: T(v) for k, v in g.items() if k.startswith(name + "_sd_")})
+    mod = mod.cuda().eval()
+    with torch.no_grad():
+        new_xyz, feats, inds = mod(T(g[name + "_xyz"]).cuda(), T(g[name + "_feats"]).cuda())
+    assert np.array_equal(inds.cpu().numpy(), g[name + "_inds"])
+    assert np.array_equal(new_xyz.cpu().numpy(), g[name + "_new_xyz"])
+    assert_features(feats, T(g[name + "_new_feats"]), "fp32")
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_fp_module_vs_reference_python_golden(ref_modules_golden, fused):
+    from situation3d_b200.pointnet2.pointnet2_modules import PointnetFPModule
+    g = ref_modules_golden
+    mod = PointnetFPModule(mlp=[44, 48, 24], fused=fused, precision="fp32")
+    mod.load_state_dict({k[len("fp_sd_"):]: T(v) for k, v in g.items() if k.startswith("fp_sd_")})
+    mod = mod.cuda().eval()
+    with torch.no_grad():
+        out = mod(T(g["fp_unknown"]).cuda(), T(g["fp_known"]).cuda(), T(g["fp_uf"]).cuda(), T(g["fp_kf"]).cuda())
+    assert_features(out, T(g["fp_out"]), "fp32")
+
+
+def test_query_and_group_vs_reference_python_golden(ref_modules_golden):
+    from situation3d_b200.pointnet2.pointnet2_utils import QueryAndGroup
+    g = ref_modules_golden
+    grouper = QueryAndGroup(0.8, 12, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
+    nf, gx = grouper(T(g["qg_xyz"]).cuda(), T(g["qg_new_xyz"]).cuda(), T(g["qg_feats"]).cuda())
+    torch.testing.assert_close(nf.cpu(), T(g["qg_out"]), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(gx.cpu(), T(g["qg_gxyz"]), rtol=1e-6, atol=1e-6)
+
+
+# ---- modules against the oracle wiring on seeded inputs -------------------------------------------
+
+def _module_case(seed, n, c):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(2, n, 3, generator=g), torch.randn(2, c, n, generator=g).relu()
+
+
+@pytest.mark.parametrize("precision", precisions())
+@pytest.mark.parametrize("npoint,radius,nsample,mlp,n", [
+    (256, 0.45, 64, [129, 64, 64, 128], 3000),       # SA1 shape
+    (128, 0.8, 32, [128, 128, 128, 256], 600),       # SA2 shape
+    (64, 1.2, 16, [256, 128, 128, 256], 300),        # SA3/SA4 shape
+])
+def test_sa_module_vs_oracle(precision, npoint, radius, nsample, mlp, n):
+    from situation3d_b200.pointnet2.pointnet2_modules import PointnetSAModuleVotes
+    from situation3d_b200.synthetic import randomize_bn_stats
+    torch.manual_seed(1)
+    mod = randomize_bn_stats(PointnetSAModuleVotes(npoint=npoint, radius=radius, nsample=nsample, mlp=list(mlp),
+                                                   normalize_xyz=True, precision=precision)).eval()
+    xyz, feats = _module_case(11, n, mlp[0])
+    sd = {k: v.clone() for k, v in mod.state_dict().items()}
+    want_xyz, want_feats, want_inds, _ = orc.sa_module_votes(xyz, feats, sd, "", npoint, radius, nsample,
+                                                             use_xyz=True, normalize_xyz=True)
+    mod = mod.cuda()
+    with torch.no_grad():
+        new_xyz, out, inds = mod(xyz.cuda(), feats.cuda())
+    assert torch.equal(inds.cpu(), want_inds)
+    assert torch.equal(new_xyz.cpu(), want_xyz)
+    assert_features(out, want_feats, precision)
+
+
+@pytest.mark.parametrize("precision", precisions())
+def test_fp_module_vs_oracle(precision):
+    from situation3d_b200.pointnet2.pointnet2_modules import PointnetFPModule
+    from situation3d_b200.synthetic import randomize_bn_stats
+    torch.manual_seed(2)
+    mod = randomize_bn_stats(PointnetFPModule(mlp=[512, 256, 256], precision=precision)).eval()
+    g = torch.Generator().manual_seed(5)
+    unknown, known = torch.randn(2, 300, 3, generator=g), torch.randn(2, 100, 3, generator=g)
+    uf, kf = torch.randn(2, 256, 300, generator=g).relu(), torch.randn(2, 256, 100, generator=g).relu()
+    want = orc.fp_module(unknown, known, uf, kf, {k: v.clone() for k, v in mod.state_dict().items()}, "")
+    mod = mod.cuda()
+    with torch.no_grad():
+        out = mod(unknown.cuda(), known.cuda(), uf.cuda(), kf.cuda())
+    assert_features(out, want, precision)
+
+
+def test_training_mode_path_and_gradients():
+    """Training mode runs operator by operator with autograd through the *_grad kernels; its forward
+    equals the reference wiring evaluated in training mode by the oracle's torch restatement."""
+    from situation3d_b200.pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+    torch.manual_seed(3)
+    sa = PointnetSAModuleVotes(npoint=32, radius=0.7, nsample=8, mlp=[5, 16, 32], normalize_xyz=True).cuda().train()
+    fp = PointnetFPModule(mlp=[32 + 5, 16]).cuda().train()
+    xyz, feats = _module_case(21, 200, 5)
+    xyz, feats = xyz.cuda(), feats.cuda().requires_grad_(True)
+    new_xyz, out, inds = sa(xyz, feats)
+    up = fp(xyz, new_xyz, feats, out)
+    loss = up.square().mean()
+    loss.backward()
+    assert feats.grad is not None and torch.isfinite(feats.grad).all() and feats.grad.abs().sum() > 0
+    assert all(p.grad is not None for p in list(sa.parameters()) + list(fp.parameters()))
+    # finite-difference check of d loss / d feats along a random direction (fp32: loose tolerance)
+    d = torch.randn_like(feats)
+    eps = 1e-2
+    with torch.no_grad():
+        def f(x):
+            nx, o, _ = sa(xyz, x, inds)
+            return fp(xyz, nx, x, o).square().mean()
+        num = (f(feats + eps * d) - f(feats - eps * d)) / (2 * eps)
+    ana = (feats.grad * d).sum()
+    assert abs(float(num) - float(ana)) <= 0.15 * max(abs(float(ana)), 1e-3) + 1e-4
+
+
+# ---- backbone ------------------------------------------------------------------------------------
+
+def _backbone_pair(precision, n_points, npoints, seed=0, batch=2, feat=129):
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=feat, precision=precision, npoints=npoints)).eval()
+    pc = torch.from_numpy(make_batch(batch, n_points, feat, first_seed=seed))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    layers = tuple((name, npnt, r, ns) for (name, _, r, ns), npnt in zip(orc.BACKBONE_LAYERS, npoints))
+    return net, pc, sd, layers
+
+
+def _check_backbone(out, want, precision):
+    for k in ("sa1", "sa2", "sa3", "sa4"):
+        assert torch.equal(out[k + "_inds"].cpu(), want[k + "_inds"]), k
+        assert torch.equal(out[k + "_xyz"].cpu(), want[k + "_xyz"]), k
+        assert_features(out[k + "_features"], want[k + "_features"], precision)
+    assert torch.equal(out["fp2_inds"].cpu(), want["fp2_inds"])
+    assert torch.equal(out["fp2_xyz"].cpu(), want["fp2_xyz"])
+    assert_features(out["fp2_features"], want["fp2_features"], precision)
+
+
+@pytest.mark.parametrize("precision", precisions())
+def test_backbone_small_vs_oracle(precision):
+    net, pc, sd, layers = _backbone_pair(precision, 4000, (512, 256, 128, 64))
+    want = orc.backbone(pc, sd, layers)
+    with torch.no_grad():
+        out = net.cuda()({"point_clouds": pc.cuda()})
+    _check_backbone(out, want, precision)
+    assert out["fp2_features"].shape == (2, 256, 256)
+
+
+@pytest.mark.parametrize("precision", precisions())
+def test_backbone_full_size_vs_oracle(precision):
+    """BASELINE.json config: 40k points, 129 feature channels, SA 2048/1024/512/256."""
+    net, pc, sd, layers = _backbone_pair(precision, 40000, (2048, 1024, 512, 256), seed=7, batch=1)
+    want = orc.backbone(pc, sd, layers)
+    with torch.no_grad():
+        out = net.cuda()({"point_clouds": pc.cuda()})
+    _check_backbone(out, want, precision)
+    assert out["fp2_features"].shape == (1, 256, 1024)
+    assert torch.equal(out["fp2_inds"], out["sa1_inds"][:, :1024])
+
+
+def test_backbone_fused_equals_unfused_full_size():
+    net, pc, _, _ = _backbone_pair("fp32", 40000, (2048, 1024, 512, 256), seed=9, batch=2)
+    net = net.cuda()
+    with torch.no_grad():
+        a = net({"point_clouds": pc.cuda()})
+        net.fused = False
+        for m in (net.sa1, net.sa2, net.sa3, net.sa4, net.fp1, net.fp2):
+            m.fused = False
+        b = net({"point_clouds": pc.cuda()})
+    for k in ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds"):
+        assert torch.equal(a[k], b[k])
+    assert_features(a["fp2_features"], b["fp2_features"], "fp32")
+
+
+# ---- situation re-encoding -----------------------------------------------------------------------
+
+def test_situation_helpers_vs_reference_python_golden(ref_modules_golden):
+    from situation3d_b200 import reencode as re
+    g = ref_modules_golden
+    torch.testing.assert_close(re.quaternions_to_rotation_matrices(T(g["sit_quats"]).cuda()).cpu(), T(g["sit_quat_R"]),
+                               rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(re.batch_rotation_vector_to_matrix(T(g["sit_rotvec"]).cuda()).cpu(),
+                               T(g["sit_rotvec_R"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(re.batch_matrix_function(T(g["sit_vec"]).cuda()).cpu(), T(g["sit_M"]),
+                               rtol=1e-5, atol=1e-6)
+    w = [T(g["sit_pe_" + k]).cuda() for k in ("0.weight", "0.bias", "2.weight", "2.bias")]
+    out, new_pos, prior = re.reencode_tokens(T(g["sit_tokens"]).cuda(), T(g["sit_pos"]).cuda(), T(g["sit_vec"]).cuda(), *w)
+    torch.testing.assert_close(new_pos.cpu(), T(g["sit_pos_t"]), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(prior.cpu(), T(g["sit_prior"]), rtol=1e-4, atol=1e-7)
+    ident = torch.zeros(6, 7)
+    ident[:, 6] = 1
+    out_id, _, _ = re.reencode_tokens(T(g["sit_tokens"]).cuda(), T(g["sit_pos"]).cuda(), ident.cuda(), *w)
+    torch.testing.assert_close(out_id.cpu(), T(g["sit_tokens_pe"]), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("agent", [False, True])
+def test_reencode_vs_oracle_config3_shape(agent):
+    """BASELINE.json config 3 shape: B=32 scenes x 256 tokens x 256 channels."""
+    from situation3d_b200.reencode import SituationReencoder
+    from situation3d_b200.synthetic import make_situations
+    torch.manual_seed(4)
+    mod = SituationReencoder(to_agent_frame=agent)
+    g = torch.Generator().manual_seed(6)
+    tokens = torch.randn(32, 256, 256, generator=g)
+    pos = torch.randn(32, 256, 3, generator=g) * 2
+    sit = torch.from_numpy(make_situations(32))
+    pe = mod.pos_embed
+    want, want_pos, want_prior = orc.reencode(tokens, pos, sit, pe[0].weight.detach(), pe[0].bias.detach(),
+                                              pe[2].weight.detach(), pe[2].bias.detach(), to_agent_frame=agent)
+    mod = mod.cuda()
+    d = mod({"scene_feat": tokens.cuda(), "scene_positions": pos.cuda(), "auxiliary_task": sit.cuda()})
+    torch.testing.assert_close(d["scene_feat"].cpu(), want, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(d["scene_positions_agent"].cpu(), want_pos, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(d["auxiliary_task_loc_gt"].cpu(), want_prior, rtol=1e-3, atol=1e-7)
+    torch.testing.assert_close(d["auxiliary_task_loc_gt"].sum(1).cpu(), torch.ones(32), rtol=1e-4, atol=1e-4)
+    assert torch.equal(d["att_feat_pre"].cpu(), tokens)
+
+
+def test_reencode_roundtrip_property():
+    """Forward transform followed by the agent-frame (inverse) transform is the identity for unit quaternions."""
+    from situation3d_b200.reencode import reencode_tokens
+    from situation3d_b200.synthetic import make_situations
+    g = torch.Generator().manual_seed(8)
+    pos = (torch.randn(8, 100, 3, generator=g) * 3).cuda()
+    sit = torch.from_numpy(make_situations(8, seed=3)).cuda()
+    tok = torch.zeros(8, 100, 16).cuda()
+    w1, b1, w2, b2 = torch.zeros(4, 2).cuda(), torch.zeros(4).cuda(), torch.zeros(16, 4).cuda(), torch.zeros(16).cuda()
+    _, fwd, _ = reencode_tokens(tok, pos, sit, w1, b1, w2, b2, want_prior=False)
+    _, back, _ = reencode_tokens(tok, fwd, sit, w1, b1, w2, b2, to_agent_frame=True, want_prior=False)
+    torch.testing.assert_close(back, pos, rtol=1e-4, atol=1e-4)
