@@ -58,6 +58,16 @@ static inline float sqdist3(float ax, float ay, float az, float bx, float by, fl
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
+/* Same expression as contracted in three_nn_kernel: there nvcc (12.9, -O3, sm_100) multiplies the
+ * y term first and fuses the x term into it (SASS of oracle/_ref/interpolate_gpu.cuda.o:
+ * FMUL dy*dy; FFMA dx*dx + .; FFMA dz*dz + .).  Both are legal contractions of the source
+ * expression; the golden vectors from the reference build (tests/golden/ref_cuda_ops.npz) pin it. */
+static inline float sqdist3_yxz(float ax, float ay, float az, float bx, float by, float bz)
+{
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
 /* ------------------------------------------------------------------------
  * Furthest point sampling.
  * sampling_gpu.cu:69-173 (kernel), :175-229 (block-size dispatch),
@@ -165,7 +175,7 @@ PN2O_API void pn2o_three_nn(int b, int n, int m, const float *unknown, const flo
             double best1 = 1e40, best2 = 1e40, best3 = 1e40;
             int b1 = 0, b2 = 0, b3 = 0;
             for (int k = 0; k < m; ++k) {
-                const float d = sqdist3(u[0], u[1], u[2], kn[k * 3], kn[k * 3 + 1], kn[k * 3 + 2]);
+                const float d = sqdist3_yxz(u[0], u[1], u[2], kn[k * 3], kn[k * 3 + 1], kn[k * 3 + 2]);
                 if (d < best1) {
                     best3 = best2; b3 = b2;
                     best2 = best1; b2 = b1;
@@ -186,7 +196,8 @@ PN2O_API void pn2o_three_nn(int b, int n, int m, const float *unknown, const flo
 }
 
 /* three_interpolate.  interpolate_gpu.cu:72-101:  p1*w1 + p2*w2 + p3*w3
- * contracted as FMUL, FFMA, FFMA. */
+ * contracted as FMUL (second term), FFMA (first term), FFMA (third term) in the reference
+ * build -- pinned by tests/golden/ref_cuda_ops.npz. */
 PN2O_API void pn2o_three_interpolate(int b, int c, int m, int n, const float *points,
                                      const int *idx, const float *weight, float *out)
 {
@@ -198,7 +209,7 @@ PN2O_API void pn2o_three_interpolate(int b, int c, int m, int n, const float *po
             for (int j = 0; j < n; ++j) {
                 const int *id = idx + ((size_t)i * n + j) * 3;
                 const float *w = weight + ((size_t)i * n + j) * 3;
-                ol[j] = fmaf(pl[id[2]], w[2], fmaf(pl[id[1]], w[1], pl[id[0]] * w[0]));
+                ol[j] = fmaf(pl[id[2]], w[2], fmaf(pl[id[0]], w[0], pl[id[1]] * w[1]));
             }
         }
     }

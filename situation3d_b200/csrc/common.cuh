@@ -49,6 +49,21 @@ __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx,
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// three_nn's variant: in the reference build nvcc multiplies the y term first and fuses x, then z
+// (SASS of the reference's three_nn_kernel; pinned by tests/golden/ref_cuda_ops.npz).
+__device__ __forceinline__ float sqdist3_yxz(float ax, float ay, float az, float bx, float by, float bz)
+{
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// three_interpolate's p1*w1 + p2*w2 + p3*w3: FMUL on the second term, then the first, then the
+// third (same build, same pinning).
+__device__ __forceinline__ float interp3(float p1, float w1, float p2, float w2, float p3, float w3)
+{
+    return __fmaf_rn(p3, w3, __fmaf_rn(p1, w1, __fmul_rn(p2, w2)));
+}
+
 __device__ __forceinline__ float sqnorm3(float x, float y, float z)
 {
     return __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));

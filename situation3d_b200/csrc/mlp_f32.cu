@@ -239,7 +239,7 @@ fp_forward_f32_kernel(MlpDesc d, int n, int m, int c_known, int c_skip, const fl
                 const float *f2 = known_rows + ((size_t)bi * m + __ldg(idx + j * 3 + 1)) * c_known;
                 const float *f3 = known_rows + ((size_t)bi * m + __ldg(idx + j * 3 + 2)) * c_known;
                 for (int k = lane; k < c_known; k += 32)
-                    dst[k] = __fmaf_rn(__ldg(f3 + k), w3, __fmaf_rn(__ldg(f2 + k), w2, __fmul_rn(__ldg(f1 + k), w1)));
+                    dst[k] = interp3(__ldg(f1 + k), w1, __ldg(f2 + k), w2, __ldg(f3 + k), w3);
                 kend = c_known;
             }
             if (c_skip > 0) {

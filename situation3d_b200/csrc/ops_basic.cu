@@ -73,7 +73,7 @@ group_points_grad_kernel(int c, int n, long long total, const float *__restrict_
         atomicAdd(grad_points + (bi * c + l) * n + a, __ldg(grad_out + (bi * c + l) * total + t));
 }
 
-// out[b,l,j] = p[l,i1]*w1 + p[l,i2]*w2 + p[l,i3]*w3 as FMUL,FFMA,FFMA
+// out[b,l,j] = p[l,i1]*w1 + p[l,i2]*w2 + p[l,i3]*w3 in the reference build's contraction order
 // (reference: interpolate_gpu.cu:72-101)
 __global__ void __launch_bounds__(kThreads)
 three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points,
@@ -90,8 +90,7 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points,
     const int c1 = min(c, c0 + kChunk);
     for (int l = c0; l < c1; ++l) {
         const float *p = points + (bi * c + l) * m;
-        out[(bi * c + l) * n + j] =
-            __fmaf_rn(__ldg(p + i3), w3, __fmaf_rn(__ldg(p + i2), w2, __fmul_rn(__ldg(p + i1), w1)));
+        out[(bi * c + l) * n + j] = interp3(__ldg(p + i1), w1, __ldg(p + i2), w2, __ldg(p + i3), w3);
     }
 }
 

@@ -130,7 +130,7 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
         __syncthreads();
         for (int t = 0; t < len; ++t) {
             const float4 pt = tile[t];
-            const float d = sqdist3(ux, uy, uz, pt.x, pt.y, pt.z);   // interpolate_gpu.cu:33-34
+            const float d = sqdist3_yxz(ux, uy, uz, pt.x, pt.y, pt.z);   // interpolate_gpu.cu:33-34
             const int k = base + t;
             if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
             else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }

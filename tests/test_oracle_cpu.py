@@ -99,6 +99,14 @@ def _d2(a, b):
     return np.float32(np.float64(d[2]) * np.float64(d[2]) + np.float64(acc))
 
 
+def _d2_yxz(a, b):
+    # three_nn's contraction in the reference build: FMUL on the y term, then x, then z
+    d = (a.astype(np.float32) - b.astype(np.float32)).astype(np.float32)
+    acc = np.float32(d[1] * d[1])
+    acc = np.float32(np.float64(d[0]) * np.float64(d[0]) + np.float64(acc))
+    return np.float32(np.float64(d[2]) * np.float64(d[2]) + np.float64(acc))
+
+
 def test_ball_query_first_principles():
     rng = np.random.default_rng(1)
     xyz = rng.normal(size=(1, 50, 3)).astype(np.float32)
@@ -152,7 +160,7 @@ def test_three_nn_first_principles():
     k = rng.normal(size=(1, 9, 3)).astype(np.float32)
     d2, idx = orc.three_nn(T(u), T(k))
     for j in range(6):
-        d = np.array([_d2(u[0, j], k[0, i]) for i in range(9)])
+        d = np.array([_d2_yxz(u[0, j], k[0, i]) for i in range(9)])
         order = np.argsort(d, kind="stable")[:3]
         assert idx[0, j].tolist() == order.tolist()
         assert np.array_equal(d2[0, j].numpy(), d[order])
