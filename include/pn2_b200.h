@@ -151,6 +151,36 @@ int pn2_sa_forward_f32(int b, int n, int npoint, int nsample, int c, const float
                        const int *idx, int nlayers, const int *dims, const void *image, float *out,
                        float *out_rows, pn2_stream_t stream);
 
+/* ---- fused set-abstraction layer on tcgen05 tensor cores (bf16 operands, fp32 accumulate) ----
+ * Same chain as pn2_sa_forward_f32 (QueryAndGroup gather -> 3-layer SharedMLP -> max-pool) with the
+ * three 1x1-conv layers as tcgen05.mma tiles whose accumulators live in TMEM.
+ *   table: bf16 channel-last rows (b, n, pn2_sa_tc_row_elems(c)), made by pn2_sa_tc_pack_rows (from
+ *          channel-last f32, e.g. point_clouds + 3 with src_ld = 3 + c and src_batch_stride = n*src_ld)
+ *          or pn2_sa_tc_pack_channels (from the reference's (b,c,n) layout), or produced as out_table
+ *          by the previous layer;
+ *   weight image: pn2_sa_tc_pack_weights from the BatchNorm-folded w1 (c1, 3+c) [xyz columns first, the
+ *          reference's channel order], w2 (c2,c1), w3 (c3,c2) and biases (device pointers, f32);
+ *   out (b,c3,npoint) f32; out_table (b,npoint,c3) bf16 or NULL.
+ * Supported shapes (pn2_sa_tc_supported): use_xyz, exactly three layers, c1,c2 multiples of 16 up to
+ * 256, c3 = 128 or 256, nsample in {16,32,64,128}, npoint*nsample a multiple of 128.  Other shapes
+ * run through pn2_sa_forward_f32. */
+int pn2_sa_tc_row_elems(int c);
+int pn2_sa_tc_supported(int c, int c1, int c2, int c3, int npoint, int nsample);
+size_t pn2_sa_tc_weight_image_bytes(int c, int c1, int c2, int c3);
+int pn2_sa_tc_pack_weights(int c, int c1, int c2, int c3, const float *w1, const float *b1,
+                           const float *w2, const float *b2, const float *w3, const float *b3,
+                           void *image, pn2_stream_t stream);
+int pn2_sa_tc_pack_rows(int b, int n, int c, const float *src, long long src_batch_stride, int src_ld,
+                        void *table, pn2_stream_t stream);
+int pn2_sa_tc_pack_channels(int b, int c, int n, const float *features, void *table, pn2_stream_t stream);
+int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, int c1, int c2, int c3,
+                      float inv_radius, const float *xyz, const float *new_xyz, const void *table,
+                      const int *idx, const void *weight_image, float *out, void *out_table,
+                      pn2_stream_t stream);
+/* Diagnostic: D (128 x n f32) = A (128 x k bf16) * B^T (n x k bf16) through the same shared-memory
+ * layouts, descriptors and TMEM path as the fused kernel (one tile).  n, k multiples of 16. */
+int pn2_selftest_umma(int n, int k, const void *a, const void *b, float *d, pn2_stream_t stream);
+
 /* Fused feature-propagation layer, fp32.  Replaces PointnetFPModule.forward
  * (pointnet2_modules.py:399-421) in eval mode after three_nn: sqrt -> 1/(d+1e-8) ->
  * normalise -> three_interpolate -> cat(skip) -> SharedMLP.

@@ -54,6 +54,14 @@ _PROTOTYPES = {
     "pn2_rows_from_channels": (_i, [_i, _i, _i, _p, _p, _p]),
     "pn2_sa_forward_f32": (_i, [_i, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _p, _i, POINTER(_i), _p, _p, _p, _p]),
     "pn2_fp_forward_f32": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, POINTER(_i), _p, _p, _p, _p]),
+    "pn2_sa_tc_row_elems": (_i, [_i]),
+    "pn2_sa_tc_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "pn2_sa_tc_weight_image_bytes": (c_size_t, [_i, _i, _i, _i]),
+    "pn2_sa_tc_pack_weights": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_sa_tc_pack_rows": (_i, [_i, _i, _i, _p, ctypes.c_longlong, _i, _p, _p]),
+    "pn2_sa_tc_pack_channels": (_i, [_i, _i, _i, _p, _p, _p]),
+    "pn2_sa_tc_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_selftest_umma": (_i, [_i, _i, _p, _p, _p, _p]),
     "pn2_quaternions_to_rotation_matrices": (_i, [_i, _p, _p, _p]),
     "pn2_rotation_vectors_to_matrices": (_i, [_i, _p, _p, _p]),
     "pn2_situation_matrices": (_i, [_i, _p, _p, _p]),

@@ -6,23 +6,28 @@
 // __syncthreads tree.  FPS is a chain of m-1 dependent argmax rounds, so what matters is
 // the latency of ONE round.  Here a scene is owned by a thread-block cluster (1..16 CTAs):
 //   - every point lives in a register slot of exactly one thread for the whole kernel
-//     (x, y, z and its running min distance), nothing is re-read from HBM/L2;
-//   - a round is: P distance updates per thread -> warp argmax with two redux.sync ->
-//     per-warp winners in shared memory, one bar.sync -> CTA winner;
-//   - CTAs exchange their winner (key + xyz, 20 bytes) with st.async straight into every
-//     peer's shared memory, completing a transaction mbarrier there: one DSMEM hop per
-//     round, no cluster-wide barrier.
+//     (x, y, z and its running min distance); nothing is re-read from HBM/L2;
+//   - a round is: P distance updates per thread -> warp argmax (one redux.sync + one ballot)
+//     -> the warp's winner (distance bits + xyz, 16 bytes) goes to shared memory;
+//   - single CTA: one bar.sync, every warp reduces the <= 16 warp winners again;
+//   - cluster: every warp sends its winner with st.async straight into the shared memory of
+//     ALL CTAs of the cluster, completing a transaction mbarrier there: one DSMEM hop per
+//     round, no bar.sync and no cluster-wide barrier; every CTA then reduces the same
+//     (#CTAs x #warps) table, so all CTAs agree on the next sample without a broadcast.
+//   - the output index is not needed by the next round: the owner thread stores its slot
+//     number and a parallel pass converts slots to point indices after the last round.
 //
 // Exactness.  The reference's argmax tie order is an artefact of its strided scan and
 // shared-memory tree: among equal maxima the winner is the thread with
 // the smallest bit-reversed id, then the smallest k inside that thread.  Points are
 // therefore laid out in "rank order" g = bitrev(k mod bs) * cnt + k div bs (bs = the
-// reference block size for this n, cnt = ceil(n / bs)), so that the reference's winner is
-// simply the candidate with the largest distance and, among equals, the smallest g.
-// Distances are non-negative floats, so their bit patterns order like unsigned integers
-// and the argmax is an integer max over (dist_bits + 1, ~g); key 0 means "no candidate"
-// (every point of the thread is skipped or a padding slot), for which the reference
-// yields index 0.
+// reference block size for this n, cnt = ceil(n / bs)), and thread t of the cluster owns
+// the contiguous slots [t*P, (t+1)*P).  The reference's winner is then the candidate with
+// the largest distance and, among equals, the smallest g -- i.e. the first slot of the
+// first lane of the first warp of the first CTA, which is what "strict > in slot order",
+// ffs(ballot) and the table order compute.  Distances are non-negative floats, so their
+// bit patterns order like unsigned integers; key 0 means "no candidate" (every slot of the
+// thread is a skipped point or padding), for which the reference yields index 0.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -93,7 +98,9 @@ __device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_
 }
 
 constexpr int kMaxCluster = 16;
+constexpr int kMaxWarps = 16;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kNoSlot = 0xffffffffu;
 
 // rank-order slot g -> original point index k (or -1 for a padding slot)
 __device__ __forceinline__ int unrank(uint32_t g, int lg_bs, int cnt, int n)
@@ -108,31 +115,31 @@ __device__ __forceinline__ int unrank(uint32_t g, int lg_bs, int cnt, int n)
 
 // P = point slots per thread.  REGS: xyz of the slots are kept in registers (P <= 16);
 // otherwise they are read back from this CTA's shared-memory copy each round.
-template <int P, bool REGS, int MAXT>
+// CLUSTER: compiled-in switch between the single-CTA and the DSMEM exchange.
+template <int P, bool REGS, bool CLUSTER, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int *__restrict__ idxs,
            float *__restrict__ new_xyz)
 {
     extern __shared__ float dyn[];   // sx[P*T], sy[P*T], sz[P*T]
-    __shared__ uint2 w_key[2][32];
-    __shared__ float4 w_xyz[2][32];
-    __shared__ __align__(16) uint4 c_msg[2][kMaxCluster];   // (hi, lo, x, y) of each CTA's winner
-    __shared__ uint32_t c_z[2][kMaxCluster];
-    __shared__ __align__(8) uint64_t c_bar[2];
+    // winners table, double buffered: (distance key, x, y, z) per warp of every CTA
+    __shared__ __align__(16) uint4 table[2][kMaxCluster * kMaxWarps];
+    __shared__ __align__(8) uint64_t bar[2];
 
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
-    const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
+    const uint32_t C = CLUSTER ? cluster_nctarank() : 1u, rank = CLUSTER ? cluster_ctarank() : 0u;
     const int scene = blockIdx.x / C;
     const float *p = xyz + (size_t)scene * n * 3;
     int *out_idx = idxs + (size_t)scene * m;
     float *out_xyz = new_xyz ? new_xyz + (size_t)scene * m * 3 : nullptr;
     float *sx = dyn, *sy = dyn + P * T, *sz = dyn + 2 * P * T;
-    const uint32_t gstride = C * T, gbase = rank * T + tid;
+    const uint32_t g0 = (rank * T + tid) * P;          // first slot of this thread
+    const int entries = (int)C * W;                      // table entries per round
 
     float px[P], py[P], pz[P], pt[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-        const int k = unrank(i * gstride + gbase, lg_bs, cnt, n);
+        const int k = unrank(g0 + i, lg_bs, cnt, n);
         float x = 0.f, y = 0.f, z = 0.f, t = -1.f;   // -1: never a candidate (fminf keeps it at -1)
         if (k >= 0) {
             x = __ldg(p + 3 * (size_t)k);
@@ -144,19 +151,20 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
         px[i] = x; py[i] = y; pz[i] = z; pt[i] = t;
         sx[i * T + tid] = x; sy[i * T + tid] = y; sz[i * T + tid] = z;
     }
-    if (C > 1) {
+    if (CLUSTER) {
         if (tid == 0) {
-            mbar_init(smem_u32(&c_bar[0]), 1);
-            mbar_init(smem_u32(&c_bar[1]), 1);
+            mbar_init(smem_u32(&bar[0]), 1);
+            mbar_init(smem_u32(&bar[1]), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         cluster_sync_all();
     }
 
     // sampling_gpu.cu:85-87: the first sample is point 0, unconditionally
-    float ox = __ldg(p), oy = __ldg(p + 1), oz = __ldg(p + 2);
+    const float p0x = __ldg(p), p0y = __ldg(p + 1), p0z = __ldg(p + 2);
+    float ox = p0x, oy = p0y, oz = p0z;
     if (rank == 0 && tid == 0) {
-        out_idx[0] = 0;
+        out_idx[0] = (int)kNoSlot;                    // converted to index 0 by the final pass
         if (out_xyz) { out_xyz[0] = ox; out_xyz[1] = oy; out_xyz[2] = oz; }
     }
 
@@ -175,59 +183,64 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
             if (d2 > best) { best = d2; bi = i; }   // strict: earliest slot wins inside a thread
         }
         const uint32_t hi = best >= 0.f ? __float_as_uint(best) + 1u : 0u;
-        const uint32_t lo = ~(uint32_t)(bi * gstride + gbase);
 
-        // warp winner
-        uint32_t mh = __reduce_max_sync(kFull, hi);
-        uint32_t ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
-        if (hi == mh && lo == ml) {
-            const int s = bi * T + tid;
-            w_key[buf][warp] = make_uint2(mh, ml);
-            w_xyz[buf][warp] = make_float4(sx[s], sy[s], sz[s], 0.f);
-        }
-        __syncthreads();
-        // CTA winner (every warp computes it redundantly: no second barrier)
-        const uint2 wk = lane < W ? w_key[buf][lane] : make_uint2(0u, 0u);
-        mh = __reduce_max_sync(kFull, wk.x);
-        ml = __reduce_max_sync(kFull, wk.x == mh ? wk.y : 0u);
-        int src = __ffs(__ballot_sync(kFull, wk.x == mh && wk.y == ml)) - 1;
-        const float4 wv = w_xyz[buf][src];
-        float nx = wv.x, ny = wv.y, nz = wv.z;
-
-        if (C > 1) {
-            // cluster winner: all-to-all of 20-byte messages through DSMEM
-            const uint32_t bar = smem_u32(&c_bar[buf]);
-            if (warp == 0 && lane < C) {
-                const uint32_t rbar = map_to_cta(bar, lane);
-                st_async_v4(map_to_cta(smem_u32(&c_msg[buf][rank]), lane), mh, ml,
-                            __float_as_uint(nx), __float_as_uint(ny), rbar);
-                st_async_b32(map_to_cta(smem_u32(&c_z[buf][rank]), lane), __float_as_uint(nz), rbar);
+        // warp winner: largest key, lowest lane among equals
+        const uint32_t wmax = __reduce_max_sync(kFull, hi);
+        const int wsrc = __ffs(__ballot_sync(kFull, hi == wmax)) - 1;
+        const bool warp_owner = lane == wsrc;
+        if (!CLUSTER) {
+            if (warp_owner) {
+                const int s = bi * T + tid;
+                table[buf][warp] = make_uint4(wmax, __float_as_uint(sx[s]), __float_as_uint(sy[s]),
+                                              __float_as_uint(sz[s]));
             }
-            if (tid == 0) mbar_arrive_expect_tx(bar, 20u * C);
-            mbar_wait(bar, (r >> 1) & 1);
-            const uint4 e = lane < C ? c_msg[buf][lane] : make_uint4(0u, 0u, 0u, 0u);
-            mh = __reduce_max_sync(kFull, e.x);
-            ml = __reduce_max_sync(kFull, e.x == mh ? e.y : 0u);
-            src = __ffs(__ballot_sync(kFull, e.x == mh && e.y == ml)) - 1;
-            nx = __uint_as_float(__shfl_sync(kFull, e.z, src));
-            ny = __uint_as_float(__shfl_sync(kFull, e.w, src));
-            nz = __uint_as_float(c_z[buf][src]);
-        }
-
-        int k = 0;
-        if (mh != 0u) {
-            k = unrank(~ml, lg_bs, cnt, n);
-            ox = nx; oy = ny; oz = nz;
+            __syncthreads();
         } else {
-            // every point skipped: the reference's reduction leaves besti = 0 (sampling_gpu.cu:93-94,170)
-            ox = __ldg(p); oy = __ldg(p + 1); oz = __ldg(p + 2);
+            // every warp publishes its winner to all CTAs of the cluster (lane c -> CTA c)
+            const uint32_t mb = smem_u32(&bar[buf]);
+            const int s = bi * T + tid;
+            const uint32_t vx = __shfl_sync(kFull, __float_as_uint(sx[s]), wsrc);
+            const uint32_t vy = __shfl_sync(kFull, __float_as_uint(sy[s]), wsrc);
+            const uint32_t vz = __shfl_sync(kFull, __float_as_uint(sz[s]), wsrc);
+            if (lane < C)
+                st_async_v4(map_to_cta(smem_u32(&table[buf][rank * W + warp]), lane), wmax, vx, vy, vz,
+                            map_to_cta(mb, lane));
+            if (tid == 0) mbar_arrive_expect_tx(mb, 16u * entries);
+            mbar_wait(mb, (r >> 1) & 1);
         }
-        if (rank == 0 && tid == 0) {
-            out_idx[j] = k;
+        // winner of the whole scene: every warp reduces the same table (entries <= 256)
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        int eslot = lane;
+        for (int q = lane; q < entries; q += 32) {       // ascending slots: '>' keeps the earliest
+            const uint4 v = table[buf][q];
+            if (v.x > e.x) { e = v; eslot = q; }
+        }
+        const uint32_t smax = __reduce_max_sync(kFull, e.x);
+        // among lanes holding the maximum the smallest table slot wins (slot order = point order)
+        const uint32_t cand = e.x == smax ? (uint32_t)eslot : 0xffffu;
+        const uint32_t sslot = __reduce_min_sync(kFull, cand);
+        const int ssrc = __ffs(__ballot_sync(kFull, cand == sslot)) - 1;
+        const float nx = __uint_as_float(__shfl_sync(kFull, e.y, ssrc));
+        const float ny = __uint_as_float(__shfl_sync(kFull, e.z, ssrc));
+        const float nz = __uint_as_float(__shfl_sync(kFull, e.w, ssrc));
+
+        const bool none = smax == 0u;   // every point skipped: the reference's reduction leaves besti = 0
+        ox = none ? p0x : nx; oy = none ? p0y : ny; oz = none ? p0z : nz;
+        // the thread that owns the winning slot records it (off the critical path)
+        if (warp_owner && (int)sslot == (int)(rank * W + warp)) {
+            out_idx[j] = none ? (int)kNoSlot : (int)(g0 + bi);
             if (out_xyz) { out_xyz[3 * j] = ox; out_xyz[3 * j + 1] = oy; out_xyz[3 * j + 2] = oz; }
         }
     }
-    if (C > 1) cluster_sync_all();   // no CTA leaves while a peer may still address its shared memory
+    if (CLUSTER) cluster_sync_all();   // no CTA leaves while a peer may still address its shared memory
+    else __syncthreads();
+    // slots -> point indices (the stores above were made by threads of this cluster)
+    __threadfence();
+    if (CLUSTER) cluster_sync_all();
+    for (int j = rank * T + tid; j < m; j += C * T) {
+        const uint32_t g = (uint32_t)out_idx[j];
+        out_idx[j] = g == kNoSlot ? 0 : unrank(g, lg_bs, cnt, n);
+    }
 }
 
 struct FpsPlan {
@@ -255,9 +268,10 @@ static bool make_plan(int n, FpsPlan *pl)
     else if (slots <= 4096) { cluster = 1; threads = 256; }
     else if (slots <= 8192) { cluster = 1; threads = 512; }
     else {
-        threads = 512;
+        threads = 256;
         cluster = 2;
-        while (cluster < kMaxCluster && slots > (long long)cluster * threads * 10) cluster *= 2;
+        while (cluster < kMaxCluster && slots > (long long)cluster * threads * 8) cluster *= 2;
+        if (slots > (long long)cluster * threads * 16) threads = 512;
     }
     // tuning overrides (benchmark sweeps): PN2_FPS_CLUSTER in {1,2,4,8,16}, PN2_FPS_THREADS in {128,256,512}
     if (const char *e = getenv("PN2_FPS_CLUSTER")) {
@@ -281,7 +295,7 @@ template <int P, bool REGS, int MAXT>
 static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
                   cudaStream_t stream)
 {
-    auto kern = fps_kernel<P, REGS, MAXT>;
+    auto kern = pl.cluster > 1 ? fps_kernel<P, REGS, true, MAXT> : fps_kernel<P, REGS, false, MAXT>;
     const size_t smem = (size_t)3 * P * pl.threads * sizeof(float);
     PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (pl.cluster > 8)

@@ -1,0 +1,662 @@
+// sa_tc.cu -- fused set-abstraction layer on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+// Replaces, for eval-mode PointnetSAModuleVotes(use_xyz=True, pooling='max') with a 3-layer
+// SharedMLP, the reference chain
+//   QueryAndGroup.forward  pointnet2_utils.py:348-359  (group xyz, recentre, /radius, group feats, cat)
+//   SharedMLP              pytorch_utils.py:11-36,67-121 (3 x [1x1 conv, BatchNorm, ReLU])
+//   F.max_pool2d           pointnet2_modules.py:259-262
+// by one kernel.  A CTA works on tiles of 128 rows (row = one neighbour sample of one centre):
+//
+//   gather   cp.async (16-byte chunks) copies the neighbours' bf16 feature rows from the channel-last
+//            row table straight into the K-major, 128B-swizzled operand layout tcgen05 reads; one
+//            more chunk per row holds the recentred, normalised xyz as a bf16 hi/lo pair plus two
+//            constant 1.0 slots that carry the layer-1 bias (hi/lo) through the GEMM.
+//   layer 1  D1[s][c] = A0[s][k] W1[c][k]      tcgen05.mma, M = 128 samples, N = C1, acc in TMEM
+//   epi 1    tcgen05.ld -> ReLU -> bf16 -> the same shared-memory region, again K-major swizzled
+//   layer 2  D2[s][c] = A1[s][k] W2[c][k]
+//   epi 2    + bias, ReLU -> bf16 -> shared memory
+//   layer 3  D3[c][s] = W3[c][k] A2[s][k]      operands swapped: M = 128 channels, N = 128 samples,
+//            so that a TMEM lane is a channel and the max over nsample is a running max over the
+//            registers of ONE thread -- no cross-lane traffic
+//   epi 3    max over each centre's nsample columns, + bias, ReLU (both commute with max),
+//            fp32 (B,C3,npoint) for the API and bf16 channel-last rows for the next layer.
+//
+// The (B, C+3, npoint, nsample) tensor the reference materialises (69 MB per scene at SA1) and its
+// three activation round trips never exist; HBM sees the row table once (through L2) and the
+// pooled output.  Weights stay resident in shared memory for the lifetime of the CTA; when
+// W1+W2+W3 and the gather buffer do not fit in 227 KB together (C = 256 layers) W3 is re-staged per
+// tile into the part of the gather buffer that layer 1 has released.
+//
+// Precision: bf16 operands, fp32 accumulation (kind::f16); indices come from the fp32 kernels.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace pn2 {
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot)
+{
+    const uint32_t cols = COLS;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr)
+{
+    const uint32_t cols = COLS;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> f32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- K-major operand tiles ------------------------------------------------------------------------
+// A `rows` x K bf16 operand (K multiple of 16) is stored as K/64 tiles of [rows][64] in the canonical
+// 128-byte-swizzle K-major layout (row pitch 128 B, 8-row groups of 1024 B, 16-byte chunk index XORed
+// with row%8) followed by (K%64)/16 tiles of [rows][16] in the 32-byte-swizzle layout (row pitch 32 B,
+// 8-row groups of 256 B, chunk index XORed with (row/4)%2).  One tcgen05.mma consumes K = 16.
+__host__ __device__ inline uint32_t kop_bytes(int rows, int K) { return (uint32_t)rows * (128u * (K / 64) + 32u * ((K % 64) / 16)); }
+
+// byte offset of the 16-byte chunk that holds elements [8*ch, 8*ch + 8) of row r
+__host__ __device__ inline uint32_t kop_chunk_off(int rows, int K, int r, int ch)
+{
+    const int nfull = K / 64;
+    if (ch < nfull * 8) return (uint32_t)(ch >> 3) * rows * 128u + r * 128u + (((ch & 7) ^ (r & 7)) << 4);
+    const int t = (ch - nfull * 8) >> 1;
+    return (uint32_t)nfull * rows * 128u + (uint32_t)t * rows * 32u + r * 32u + ((((ch & 1) ^ ((r >> 2) & 1))) << 4);
+}
+
+// shared-memory matrix descriptor (SM100 format: version 1; LBO unused for swizzled K-major)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout)
+{
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+constexpr uint32_t kSw128 = 2, kSw32 = 6;
+
+// descriptor of K-step ks (16 elements) of an operand whose first row is r0 (multiple of 8)
+__device__ __forceinline__ uint64_t kop_desc(uint32_t base, int rows, int K, int ks, int r0)
+{
+    const int nfull4 = (K / 64) * 4;
+    if (ks < nfull4)
+        return smem_desc(base + (uint32_t)(ks >> 2) * rows * 128u + r0 * 128u + (ks & 3) * 32u, 1024u, kSw128);
+    return smem_desc(base + (uint32_t)(K / 64) * rows * 128u + (uint32_t)(ks - nfull4) * rows * 32u + r0 * 32u, 256u,
+                     kSw32);
+}
+
+// instruction descriptor: D f32, A/B bf16, both K-major, N at [17,23) in units of 8, M at [24,29) in units of 16
+__host__ __device__ inline uint32_t umma_idesc(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// ---- problem description --------------------------------------------------------------------------
+constexpr int kTile = 128;          // rows (samples) per tile = MMA M
+constexpr int kTcThreads = 128;
+
+struct SaTcShape {
+    int c, c1, c2, c3;      // feature channels, MLP widths
+    int row_elems;          // bf16 elements per table row = round_up(c, 8)
+    int k0;                 // layer-1 K = round_up(row_elems + 8, 16)
+    uint32_t w1_bytes, w2_bytes, w3_bytes, bias_bytes;   // image sections (bias = (c2 + c3) floats)
+    uint32_t a0_bytes, a12_bytes, region_bytes;
+    int w3_streamed;
+    uint32_t smem_bytes;
+    int tmem_cols;
+};
+
+static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool make_shape(int c, int c1, int c2, int c3, SaTcShape *s)
+{
+    if (c < 1 || c1 < 16 || c2 < 16 || c3 < 128) return false;
+    if (c1 % 16 || c2 % 16 || c3 % 128 || c1 > 256 || c2 > 256 || c3 > 256) return false;
+    s->c = c; s->c1 = c1; s->c2 = c2; s->c3 = c3;
+    s->row_elems = rup(c, 8);
+    s->k0 = rup(s->row_elems + 8, 16);
+    s->w1_bytes = kop_bytes(c1, s->k0);
+    s->w2_bytes = kop_bytes(c2, c1);
+    s->w3_bytes = kop_bytes(c3, c2);
+    s->bias_bytes = 4u * (c2 + c3);
+    s->a0_bytes = kop_bytes(kTile, s->k0);
+    s->a12_bytes = max(kop_bytes(kTile, c1), kop_bytes(kTile, c2));
+    const uint32_t budget = 225u * 1024u;
+    const uint32_t fixed = 1024u /*alignment slack*/ + s->bias_bytes + 64u;
+    uint32_t resident = s->w1_bytes + s->w2_bytes + s->w3_bytes;
+    s->w3_streamed = 0;
+    s->region_bytes = max(s->a0_bytes, s->a12_bytes);
+    if (fixed + resident + s->region_bytes > budget) {
+        s->w3_streamed = 1;
+        resident = s->w1_bytes + s->w2_bytes;
+        s->region_bytes = max(s->a0_bytes, (uint32_t)rup((int)s->a12_bytes, 1024) + s->w3_bytes);
+        if (fixed + resident + s->region_bytes > budget) return false;
+    }
+    s->region_bytes = rup((int)s->region_bytes, 1024);
+    s->smem_bytes = fixed + rup((int)resident, 1024) + s->region_bytes;
+    const int need = max(max(c1, c2), 128 * (c3 / 128));
+    s->tmem_cols = need <= 128 ? 128 : 256;
+    return true;
+}
+
+// ---- packing kernels ------------------------------------------------------------------------------
+// table[(b*n + p)*row_elems + k] = bf16(src[b*src_batch + p*src_ld + k]) for k < c, 0 for the padding
+__global__ void pack_rows_kernel(long long total_rows, int n, int c, int row_elems, const float *__restrict__ src,
+                                 long long src_batch, int src_ld, __nv_bfloat16 *__restrict__ table)
+{
+    const int chunks = row_elems / 8;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_rows * chunks) return;
+    const long long row = i / chunks;
+    const int ch = (int)(i - row * chunks);
+    const long long b = row / n, p = row - b * n;
+    const float *s = src + b * src_batch + p * src_ld + ch * 8;
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = ch * 8 + 2 * q;
+        v[q] = pack_bf16(k < c ? __ldg(s + 2 * q) : 0.f, k + 1 < c ? __ldg(s + 2 * q + 1) : 0.f);
+    }
+    *reinterpret_cast<uint4 *>(table + row * row_elems + ch * 8) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+// same from channel-first (b, c, n) features, through a shared-memory transpose
+__global__ void pack_channels_kernel(int c, int n, int row_elems, const float *__restrict__ src,
+                                     __nv_bfloat16 *__restrict__ table)
+{
+    __shared__ float t[32][33];
+    const size_t bi = blockIdx.z;
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int cc = c0 + i, nn = n0 + threadIdx.x;
+        t[i][threadIdx.x] = (cc < c && nn < n) ? __ldg(src + (bi * c + cc) * n + nn) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int nn = n0 + i, cc = c0 + threadIdx.x;
+        if (cc < row_elems && nn < n) table[(bi * n + nn) * row_elems + cc] = __float2bfloat16_rn(t[threadIdx.x][i]);
+    }
+}
+
+// Weight image = the exact shared-memory bytes: W1 | W2 | W3 (K-major swizzled tiles) | bias2 | bias3.
+// W1 columns: [0,c) features, [c,row_elems) zero, then xyz weights twice (for the hi and lo halves of
+// the coordinates) and the layer-1 bias split into a bf16 hi/lo pair (multiplied by the two 1.0 slots).
+__global__ void pack_weights_kernel(SaTcShape s, const float *__restrict__ w1, const float *__restrict__ b1,
+                                    const float *__restrict__ w2, const float *__restrict__ b2,
+                                    const float *__restrict__ w3, const float *__restrict__ b3,
+                                    unsigned char *__restrict__ image)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n1 = s.c1 * s.k0, n2 = s.c2 * s.c1, n3 = s.c3 * s.c2;
+    if (i < n1) {
+        const int r = i / s.k0, k = i % s.k0;
+        float v = 0.f;
+        const int e = k - s.row_elems;   // index inside the extras chunk
+        if (k < s.c) v = w1[(size_t)r * (s.c + 3) + 3 + k];            // reference order: xyz first
+        else if (e >= 0 && e < 3) v = w1[(size_t)r * (s.c + 3) + e];
+        else if (e >= 3 && e < 6) v = w1[(size_t)r * (s.c + 3) + e - 3];
+        else if (e == 6) v = b1 ? b1[r] : 0.f;
+        else if (e == 7) { const float b = b1 ? b1[r] : 0.f; v = b - __bfloat162float(__float2bfloat16_rn(b)); }
+        *reinterpret_cast<__nv_bfloat16 *>(image + kop_chunk_off(s.c1, s.k0, r, k >> 3) + (k & 7) * 2) =
+            __float2bfloat16_rn(v);
+    } else if (i < n1 + n2) {
+        const int j = i - n1, r = j / s.c1, k = j % s.c1;
+        *reinterpret_cast<__nv_bfloat16 *>(image + s.w1_bytes + kop_chunk_off(s.c2, s.c1, r, k >> 3) + (k & 7) * 2) =
+            __float2bfloat16_rn(w2[(size_t)r * s.c1 + k]);
+    } else if (i < n1 + n2 + n3) {
+        const int j = i - n1 - n2, r = j / s.c2, k = j % s.c2;
+        *reinterpret_cast<__nv_bfloat16 *>(image + s.w1_bytes + s.w2_bytes + kop_chunk_off(s.c3, s.c2, r, k >> 3) +
+                                           (k & 7) * 2) = __float2bfloat16_rn(w3[(size_t)r * s.c2 + k]);
+    } else if (i < n1 + n2 + n3 + s.c2 + s.c3) {
+        const int j = i - n1 - n2 - n3;
+        float *bias = reinterpret_cast<float *>(image + s.w1_bytes + s.w2_bytes + s.w3_bytes);
+        bias[j] = j < s.c2 ? (b2 ? b2[j] : 0.f) : (b3 ? b3[j - s.c2] : 0.f);
+    }
+}
+
+// ---- the fused kernel -----------------------------------------------------------------------------
+struct SaTcParams {
+    SaTcShape s;
+    int n, npoint, tiles_per_scene, ntiles;
+    float inv_radius;
+    const float *xyz, *new_xyz;
+    const __nv_bfloat16 *table;
+    const int *idx;
+    const unsigned char *image;
+    float *out;
+    __nv_bfloat16 *out_table;
+};
+
+// ReLU + bf16 pack of 32 accumulator columns into four 16-byte chunks of row `row`
+__device__ __forceinline__ void store_act32(unsigned char *dst_base, int K, int row, int col0, const uint32_t (&v)[32],
+                                            const float *bias)
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int j = q * 8 + h * 2;
+            float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+            if (bias) { a += bias[col0 + j]; b += bias[col0 + j + 1]; }
+            w[h] = pack_bf16(fmaxf(a, 0.f), fmaxf(b, 0.f));
+        }
+        *reinterpret_cast<uint4 *>(dst_base + kop_chunk_off(kTile, K, row, (col0 >> 3) + q)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <int NS, int TMEM_COLS>
+__global__ void __launch_bounds__(kTcThreads)
+sa_tc_kernel(const SaTcParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const SaTcShape &s = p.s;
+    // carve-up (1024-byte aligned operand areas)
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    unsigned char *base = smem_raw + pad;
+    const uint32_t resident = s.w1_bytes + s.w2_bytes + (s.w3_streamed ? 0u : s.w3_bytes);
+    unsigned char *w1s = base, *w2s = base + s.w1_bytes;
+    unsigned char *region = base + ((resident + 1023u) & ~1023u);
+    unsigned char *w3s = s.w3_streamed ? region + ((s.a12_bytes + 1023u) & ~1023u) : base + s.w1_bytes + s.w2_bytes;
+    float *bias2 = reinterpret_cast<float *>(region + s.region_bytes);
+    float *bias3 = bias2 + s.c2;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(bias3 + s.c3);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
+    __shared__ int s_idx[kTile];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // one-time: weights + biases into shared memory, barrier, TMEM
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.image);
+        const uint32_t nres = resident / 16;
+        for (uint32_t i = tid; i < nres; i += kTcThreads) cp_async16(smem_u32(base) + i * 16, src + i);
+        const float *bsrc = reinterpret_cast<const float *>(p.image + s.w1_bytes + s.w2_bytes + s.w3_bytes);
+        for (int i = tid; i < s.c2 + s.c3; i += kTcThreads) bias2[i] = __ldg(bsrc + i);
+        if (tid == 0) {
+            tc_mbar_init(smem_u32(mbar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+        cp_async_wait_all();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const uint32_t a_base = smem_u32(region), w1_base = smem_u32(w1s), w2_base = smem_u32(w2s),
+                   w3_base = smem_u32(w3s);
+    const uint32_t idesc1 = umma_idesc(kTile, s.c1), idesc2 = umma_idesc(kTile, s.c2), idesc3 = umma_idesc(128, kTile);
+    const int nchunk = s.row_elems / 8;          // table chunks per row
+    const int xchunk = nchunk;                   // the extras chunk
+    const int k0chunks = s.k0 / 8;
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int bi = tile / p.tiles_per_scene;
+        const int row0 = (tile - bi * p.tiles_per_scene) * kTile;      // first (centre, sample) row of the tile
+        const int centre0 = row0 / NS;
+
+        // ---- gather ----
+        const int nb = __ldg(p.idx + (size_t)bi * p.npoint * NS + row0 + tid);
+        s_idx[tid] = nb;
+        {
+            // recentred, normalised xyz (pointnet2_utils.py:350-352) as bf16 hi + lo, two 1.0 slots for the bias
+            const float *pp = p.xyz + ((size_t)bi * p.n + nb) * 3;
+            const float *cc = p.new_xyz + ((size_t)bi * p.npoint + centre0 + tid / NS) * 3;
+            float d[3], h[3], l[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                d[a] = __fmul_rn(__fsub_rn(__ldg(pp + a), __ldg(cc + a)), p.inv_radius);
+                h[a] = __bfloat162float(__float2bfloat16_rn(d[a]));
+                l[a] = d[a] - h[a];
+            }
+            *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, tid, xchunk)) =
+                make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], l[0]), pack_bf16(l[1], l[2]), pack_bf16(1.f, 1.f));
+            for (int ch = xchunk + 1; ch < k0chunks; ++ch)
+                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, tid, ch)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        for (int r = warp; r < kTile; r += kTcThreads / 32) {
+            const __nv_bfloat16 *src = p.table + ((size_t)bi * p.n + s_idx[r]) * s.row_elems;
+            for (int ch = lane; ch < nchunk; ch += 32)
+                cp_async16(a_base + kop_chunk_off(kTile, s.k0, r, ch), src + ch * 8);
+        }
+        cp_async_wait_all();
+        fence_proxy_async();
+        __syncthreads();
+
+        // ---- layer 1 ----
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < s.k0 / 16; ++ks)
+                umma_bf16(tmem, kop_desc(a_base, kTile, s.k0, ks, 0), kop_desc(w1_base, s.c1, s.k0, ks, 0), idesc1, ks > 0);
+            umma_commit(smem_u32(mbar));
+        }
+        tc_mbar_wait(smem_u32(mbar), phase);
+        phase ^= 1;
+        tc_fence_after();
+        if (s.w3_streamed) {   // the gather buffer is free now: stage W3 behind the activation area
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.image + s.w1_bytes + s.w2_bytes);
+            for (uint32_t i = tid; i < s.w3_bytes / 16; i += kTcThreads) cp_async16(w3_base + i * 16, src + i);
+        }
+        for (int c0 = 0; c0 < s.c1; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(my_tmem + c0, v);
+            store_act32(region, s.c1, tid, c0, v, nullptr);      // layer-1 bias went through the GEMM
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+
+        // ---- layer 2 ----
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < s.c1 / 16; ++ks)
+                umma_bf16(tmem, kop_desc(a_base, kTile, s.c1, ks, 0), kop_desc(w2_base, s.c2, s.c1, ks, 0), idesc2, ks > 0);
+            umma_commit(smem_u32(mbar));
+        }
+        tc_mbar_wait(smem_u32(mbar), phase);
+        phase ^= 1;
+        tc_fence_after();
+        for (int c0 = 0; c0 < s.c2; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(my_tmem + c0, v);
+            store_act32(region, s.c2, tid, c0, v, bias2);
+        }
+        if (s.w3_streamed) cp_async_wait_all();
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+
+        // ---- layer 3 (channels on the TMEM lanes) ----
+        if (tid == 0) {
+            tc_fence_after();
+            for (int mt = 0; mt < s.c3 / 128; ++mt)
+                for (int ks = 0; ks < s.c2 / 16; ++ks)
+                    umma_bf16(tmem + mt * kTile, kop_desc(w3_base, s.c3, s.c2, ks, mt * 128),
+                              kop_desc(a_base, kTile, s.c2, ks, 0), idesc3, ks > 0);
+            umma_commit(smem_u32(mbar));
+        }
+        tc_mbar_wait(smem_u32(mbar), phase);
+        phase ^= 1;
+        tc_fence_after();
+        for (int mt = 0; mt < s.c3 / 128; ++mt) {
+            const int ch = mt * 128 + tid;
+            const float bias = bias3[ch];
+            float run = -3.0e38f;
+#pragma unroll
+            for (int q = 0; q < kTile / 32; ++q) {
+                uint32_t v[32];
+                tmem_ld32(my_tmem + mt * kTile + q * 32, v);
+                if (NS >= 32) {
+                    float m = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+                    run = fmaxf(run, m);
+                    if (((q + 1) * 32) % NS == 0) {
+                        const int centre = centre0 + (q * 32) / NS;
+                        const float o = fmaxf(run + bias, 0.f);      // bias and ReLU commute with the max
+                        p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
+                        if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
+                        run = -3.0e38f;
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 32 / NS; ++g) {
+                        float m = __uint_as_float(v[g * NS]);
+#pragma unroll
+                        for (int j = 1; j < NS; ++j) m = fmaxf(m, __uint_as_float(v[g * NS + j]));
+                        const int centre = centre0 + (q * 32) / NS + g;
+                        const float o = fmaxf(m + bias, 0.f);
+                        p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
+                        if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();      // TMEM and the activation region are reused by the next tile
+    }
+    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+// ---- a one-tile GEMM through the same helpers: D (128 x n) = A (128 x k) B^T (n x k) ---------------
+// Diagnostic entry point (tests/test_tc_gpu.py): isolates descriptor/layout errors from the fusion.
+__global__ void __launch_bounds__(kTcThreads)
+umma_selftest_kernel(int n, int k, const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict__ b,
+                     float *__restrict__ d)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    unsigned char *as = base, *bs = base + ((kop_bytes(kTile, k) + 1023u) & ~1023u);
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < kTile * (k / 8); i += kTcThreads) {
+        const int r = i / (k / 8), ch = i % (k / 8);
+        *reinterpret_cast<uint4 *>(as + kop_chunk_off(kTile, k, r, ch)) = *reinterpret_cast<const uint4 *>(a + (size_t)r * k + ch * 8);
+    }
+    for (int i = tid; i < n * (k / 8); i += kTcThreads) {
+        const int r = i / (k / 8), ch = i % (k / 8);
+        *reinterpret_cast<uint4 *>(bs + kop_chunk_off(n, k, r, ch)) = *reinterpret_cast<const uint4 *>(b + (size_t)r * k + ch * 8);
+    }
+    if (tid == 0) {
+        tc_mbar_init(smem_u32(&mbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<256>(smem_u32(&tmem_slot));
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc(kTile, n);
+        for (int ks = 0; ks < k / 16; ++ks)
+            umma_bf16(tmem, kop_desc(smem_u32(as), kTile, k, ks, 0), kop_desc(smem_u32(bs), n, k, ks, 0), idesc, ks > 0);
+        umma_commit(smem_u32(&mbar));
+    }
+    tc_mbar_wait(smem_u32(&mbar), 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int j = 0; j < 32 && c0 + j < n; ++j) d[(size_t)tid * n + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+template <int NS>
+static int launch_sa_tc(const SaTcParams &p, cudaStream_t stream)
+{
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = max(1, min((int)((227u * 1024u) / (p.s.smem_bytes + 1024u)), 512 / p.s.tmem_cols));
+    const int grid = min(p.ntiles, sms * per_sm);
+    if (p.s.tmem_cols == 128) {
+        auto kern = sa_tc_kernel<NS, 128>;
+        PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.s.smem_bytes));
+        kern<<<grid, kTcThreads, p.s.smem_bytes, stream>>>(p);
+    } else {
+        auto kern = sa_tc_kernel<NS, 256>;
+        PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.s.smem_bytes));
+        kern<<<grid, kTcThreads, p.s.smem_bytes, stream>>>(p);
+    }
+    PN2_LAUNCH_CHECK("sa_tc_forward");
+    return PN2_OK;
+}
+
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_sa_tc_row_elems(int c) { return c < 0 ? 0 : rup(c, 8); }
+
+extern "C" int pn2_sa_tc_supported(int c, int c1, int c2, int c3, int npoint, int nsample)
+{
+    SaTcShape s;
+    if (!make_shape(c, c1, c2, c3, &s)) return 0;
+    if (nsample != 16 && nsample != 32 && nsample != 64 && nsample != 128) return 0;
+    if (npoint < 1 || ((long long)npoint * nsample) % kTile != 0) return 0;
+    return 1;
+}
+
+extern "C" size_t pn2_sa_tc_weight_image_bytes(int c, int c1, int c2, int c3)
+{
+    SaTcShape s;
+    if (!make_shape(c, c1, c2, c3, &s)) return 0;
+    return (size_t)s.w1_bytes + s.w2_bytes + s.w3_bytes + s.bias_bytes;
+}
+
+extern "C" int pn2_sa_tc_pack_weights(int c, int c1, int c2, int c3, const float *w1, const float *b1,
+                                      const float *w2, const float *b2, const float *w3, const float *b3,
+                                      void *image, pn2_stream_t stream)
+{
+    SaTcShape s;
+    if (!make_shape(c, c1, c2, c3, &s) || !w1 || !w2 || !w3 || !image) return PN2_ERR_INVALID_ARGUMENT;
+    const size_t bytes = (size_t)s.w1_bytes + s.w2_bytes + s.w3_bytes + s.bias_bytes;
+    PN2_CUDA_TRY(cudaMemsetAsync(image, 0, bytes, as_stream(stream)));   // padding columns and tile tails
+    const int total = s.c1 * s.k0 + s.c2 * s.c1 + s.c3 * s.c2 + s.c2 + s.c3;
+    pack_weights_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(s, w1, b1, w2, b2, w3, b3,
+                                                                             static_cast<unsigned char *>(image));
+    PN2_LAUNCH_CHECK("sa_tc_pack_weights");
+    return PN2_OK;
+}
+
+extern "C" int pn2_sa_tc_pack_rows(int b, int n, int c, const float *src, long long src_batch_stride, int src_ld,
+                                   void *table, pn2_stream_t stream)
+{
+    if (b < 0 || n < 0 || c < 1 || src_ld < c) return PN2_ERR_INVALID_ARGUMENT;
+    if (b == 0 || n == 0) return PN2_OK;
+    if (!src || !table) return PN2_ERR_INVALID_ARGUMENT;
+    const int row_elems = rup(c, 8);
+    const long long rows = (long long)b * n, work = rows * (row_elems / 8);
+    pack_rows_kernel<<<(unsigned)((work + 255) / 256), 256, 0, as_stream(stream)>>>(
+        rows, n, c, row_elems, src, src_batch_stride, src_ld, static_cast<__nv_bfloat16 *>(table));
+    PN2_LAUNCH_CHECK("sa_tc_pack_rows");
+    return PN2_OK;
+}
+
+extern "C" int pn2_sa_tc_pack_channels(int b, int c, int n, const float *features, void *table, pn2_stream_t stream)
+{
+    if (b < 0 || n < 0 || c < 1 || b > 65535) return PN2_ERR_INVALID_ARGUMENT;
+    if (b == 0 || n == 0) return PN2_OK;
+    if (!features || !table) return PN2_ERR_INVALID_ARGUMENT;
+    const int row_elems = rup(c, 8);
+    dim3 grid(ceil_div(n, 32), ceil_div(row_elems, 32), b), block(32, 8);
+    pack_channels_kernel<<<grid, block, 0, as_stream(stream)>>>(c, n, row_elems, features,
+                                                                static_cast<__nv_bfloat16 *>(table));
+    PN2_LAUNCH_CHECK("sa_tc_pack_channels");
+    return PN2_OK;
+}
+
+extern "C" int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, int c1, int c2, int c3,
+                                 float inv_radius, const float *xyz, const float *new_xyz, const void *table,
+                                 const int *idx, const void *weight_image, float *out, void *out_table,
+                                 pn2_stream_t stream)
+{
+    if (b < 0 || n < 1 || !pn2_sa_tc_supported(c, c1, c2, c3, npoint, nsample)) return PN2_ERR_INVALID_ARGUMENT;
+    if (b == 0) return PN2_OK;
+    if (!xyz || !new_xyz || !table || !idx || !weight_image || !out) return PN2_ERR_INVALID_ARGUMENT;
+    SaTcParams p;
+    make_shape(c, c1, c2, c3, &p.s);
+    p.n = n; p.npoint = npoint;
+    p.tiles_per_scene = (int)(((long long)npoint * nsample) / kTile);
+    p.ntiles = b * p.tiles_per_scene;
+    p.inv_radius = inv_radius;
+    p.xyz = xyz; p.new_xyz = new_xyz;
+    p.table = static_cast<const __nv_bfloat16 *>(table);
+    p.idx = idx;
+    p.image = static_cast<const unsigned char *>(weight_image);
+    p.out = out;
+    p.out_table = static_cast<__nv_bfloat16 *>(out_table);
+    switch (nsample) {
+    case 16: return launch_sa_tc<16>(p, as_stream(stream));
+    case 32: return launch_sa_tc<32>(p, as_stream(stream));
+    case 64: return launch_sa_tc<64>(p, as_stream(stream));
+    case 128: return launch_sa_tc<128>(p, as_stream(stream));
+    }
+    return PN2_ERR_INVALID_ARGUMENT;
+}
+
+// D (128 x n, f32 row-major) = A (128 x k, bf16 row-major) * B^T (n x k, bf16 row-major); n % 16 == 0, k % 16 == 0
+extern "C" int pn2_selftest_umma(int n, int k, const void *a, const void *b, float *d, pn2_stream_t stream)
+{
+    if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || !a || !b || !d) return PN2_ERR_INVALID_ARGUMENT;
+    const size_t smem = 2048 + ((kop_bytes(kTile, k) + 1023u) & ~1023u) + kop_bytes(n, k);
+    if (smem > 220 * 1024) return PN2_ERR_INVALID_ARGUMENT;
+    PN2_CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, kTcThreads, smem, as_stream(stream)>>>(n, k, static_cast<const __nv_bfloat16 *>(a),
+                                                                     static_cast<const __nv_bfloat16 *>(b), d);
+    PN2_LAUNCH_CHECK("selftest_umma");
+    return PN2_OK;
+}

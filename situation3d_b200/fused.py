@@ -54,17 +54,25 @@ class MlpImage:
         self.dims = None
         self.image = None
         self.folded = None
+        self.f32_only = True
+        self._f32_alt = None
 
-    def get(self, mlp, precision):
-        key = (precision,) + _mlp_state_key(mlp)
+    def get(self, mlp, precision, kind="sa"):
+        key = (precision, kind) + _mlp_state_key(mlp)
         if key != self.key:
             folded = fold_shared_mlp(mlp)
             if folded is None:
                 self.key, self.image, self.dims, self.folded = key, None, None, None
                 return None
             dims = [folded[0][0].shape[1]] + [w.shape[0] for w, _ in folded]
-            self.image = _PACKERS[precision](dims, folded)
+            self.image = _PACKERS[precision if kind == "sa" else "fp32"](dims, folded)
+            if self.image is None and precision == "bf16" and kind == "sa":
+                self.image = _pack_f32(dims, folded)      # shapes outside the tcgen05 kernel: fp32 kernel
+                self.f32_only = True
+            else:
+                self.f32_only = precision != "bf16" or kind != "sa"
             self.key, self.dims, self.folded = key, dims, folded
+            self._f32_alt = None
         return self
 
 
@@ -83,7 +91,25 @@ def _pack_f32(dims, folded):
     return image
 
 
-_PACKERS = {"fp32": _pack_f32}
+def _pack_bf16(dims, folded):
+    """Weight image of the tcgen05 SA kernel (3 layers, xyz columns first in layer 1); None when the
+    widths are outside what that kernel covers (such stacks run on the fp32 kernel)."""
+    if len(folded) != 3:
+        return None
+    c, c1, c2, c3 = dims[0] - 3, dims[1], dims[2], dims[3]
+    nbytes = lib.pn2_sa_tc_weight_image_bytes(c, c1, c2, c3)
+    if nbytes == 0:
+        return None
+    dev = folded[0][0].device
+    image = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    (w1, b1), (w2, b2), (w3, b3) = folded
+    with torch.cuda.device(dev):
+        check(lib.pn2_sa_tc_pack_weights(c, c1, c2, c3, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3),
+                                         ptr(image), stream_ptr()), "sa_tc_pack_weights")
+    return image
+
+
+_PACKERS = {"fp32": _pack_f32, "bf16": _pack_bf16}
 
 
 def rows_from_channels(features):
@@ -165,5 +191,56 @@ def fp_forward_f32(img, dist2, idx, known_rows, skip_rows, want_rows=True):
     return out, out_rows
 
 
-SA_FORWARD = {"fp32": sa_forward_f32}
-FP_FORWARD = {"fp32": fp_forward_f32}
+def bf16_rows(table, ld, c):
+    """bf16 channel-last row table (B, n, row_elems) from f32 channel-last rows (pitch ld floats)."""
+    B, n = table.shape[0], table.shape[1]
+    row_elems = lib.pn2_sa_tc_row_elems(c)
+    out = torch.empty((B, n, row_elems), dtype=torch.bfloat16, device=table.device)
+    with torch.cuda.device(table.device):
+        check(lib.pn2_sa_tc_pack_rows(B, n, c, ptr(table), n * ld, ld, ptr(out), stream_ptr()), "sa_tc_pack_rows")
+    return out
+
+
+def _f32_rows(rows):
+    return rows if rows is None or rows.dtype == torch.float32 else rows.float()
+
+
+def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True):
+    """Fused SA layer on tcgen05 (pn2_sa_tc_forward).  ``table`` is either f32 channel-last rows (packed to
+    bf16 here) or the bf16 row table a previous layer produced.  Shapes the tensor-core kernel does not
+    cover run on the fp32 kernel (with an fp32 image built on demand)."""
+    B, N, _ = xyz.shape
+    npoint, nsample = idx.shape[1], idx.shape[2]
+    dims = img.dims
+    ok = use_xyz and not img.f32_only and len(dims) == 4 and \
+        lib.pn2_sa_tc_supported(c, dims[1], dims[2], dims[3], npoint, nsample)
+    if not ok:
+        alt = img if img.f32_only else img._f32_alt
+        if alt is None:
+            alt = MlpImage()
+            alt.dims, alt.folded, alt.image = img.dims, img.folded, _pack_f32(img.dims, img.folded)
+            img._f32_alt = alt
+        rows = _f32_rows(table)
+        if rows is not table:
+            ld = rows.shape[2]
+        return sa_forward_f32(alt, xyz, new_xyz, idx, rows, ld, c, use_xyz, inv_radius, want_rows)
+    if table.dtype != torch.bfloat16:
+        table = bf16_rows(table, ld, c)
+    cout = dims[3]
+    out = torch.empty((B, cout, npoint), dtype=torch.float32, device=xyz.device)
+    out_rows = torch.empty((B, npoint, cout), dtype=torch.bfloat16, device=xyz.device) if want_rows else None
+    with torch.cuda.device(xyz.device):
+        check(lib.pn2_sa_tc_forward(B, N, npoint, nsample, c, dims[1], dims[2], dims[3], float(inv_radius), ptr(xyz),
+                                    ptr(new_xyz), ptr(table), ptr(idx), ptr(img.image), ptr(out), ptr(out_rows),
+                                    stream_ptr()), "sa_tc_forward")
+    return out, out_rows
+
+
+def fp_forward_bf16(img, dist2, idx, known_rows, skip_rows, want_rows=True):
+    """FP layers of the bf16 configuration: the interpolation + MLP kernel itself is the fp32 one (the FP
+    stack is 5% of the backbone's FLOPs); only its inputs arrive as bf16 rows from the SA kernels."""
+    return fp_forward_f32(img, dist2, idx, _f32_rows(known_rows), _f32_rows(skip_rows), want_rows)
+
+
+SA_FORWARD = {"fp32": sa_forward_f32, "bf16": sa_forward_bf16}
+FP_FORWARD = {"fp32": fp_forward_f32, "bf16": fp_forward_bf16}

@@ -230,7 +230,7 @@ class PointnetFPModule(nn.Module):
     def _fused_image(self, ref, *feats):
         if not (self.fused and ref.is_cuda and _inference_only(self, *feats)):
             return None
-        img = self._image.get(self.mlp, self.precision)
+        img = self._image.get(self.mlp, self.precision, kind="fp")
         return img if img is not None and img.image is not None else None
 
     def forward_rows(self, unknown, known, skip_rows, known_rows, img=None):
