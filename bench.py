@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--points", type=int, default=40000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end loop")
     return ap.parse_args()
 
 
@@ -342,16 +344,18 @@ def run_ours(args, rank, local_rank, world):
 
         for ev_ in consumed:
             ev_.record(main)
-        e2e_loop(W)
-        barrier()
-        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s2.record()
-        copy_stream.wait_event(s2)
-        e2e_loop(K)
-        main.wait_stream(copy_stream)
-        e2.record()
-        torch.cuda.synchronize()
-        dt_e2e = reduce_max(s2.elapsed_time(e2) * 1e-3)
+        dt_e2e = float("nan")
+        if not args.no_e2e:
+            e2e_loop(W)
+            barrier()
+            s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s2.record()
+            copy_stream.wait_event(s2)
+            e2e_loop(K)
+            main.wait_stream(copy_stream)
+            e2.record()
+            torch.cuda.synchronize()
+            dt_e2e = reduce_max(s2.elapsed_time(e2) * 1e-3)
         clocks = sampler.stop() if sampler else None
         barrier()
 
@@ -360,7 +364,7 @@ def run_ours(args, rank, local_rank, world):
             if not args.no_kernel_breakdown:
                 rows = kernel_breakdown(net, pool[0], precision, pk)
             try:
-                ref_cuda = reference_cuda_arm(pool[0], sd_cpu)
+                ref_cuda = None if args.no_reference_cuda else reference_cuda_arm(pool[0], sd_cpu)
             except Exception as ex:   # test infrastructure must not take the bench down
                 ref_cuda = {"unavailable": repr(ex)[:200]}
             if not args.no_cpu_baseline:

@@ -115,6 +115,11 @@ int pn2_group_points_grad(int b, int c, int n, int npoints, int nsample, const f
 int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *idxs,
                                     float *new_xyz, pn2_stream_t stream);
 
+/* Diagnostic: same launch as pn2_furthest_point_sampling; prof (device, 5 x int64) receives the SM cycles
+ * thread 0 of CTA 0 spent per phase of a round, summed over the m-1 rounds. */
+int pn2_debug_fps_profile(int b, int n, int m, const float *xyz, int *idxs, long long *prof,
+                          pn2_stream_t stream);
+
 /* ---- fused SharedMLP layers, full precision ------------------------------
  * A SharedMLP (pytorch_utils.py:11-36: 1x1 Conv2d without bias -> BatchNorm2d -> ReLU per
  * layer) in eval mode is described by `nlayers` and host array dims[nlayers+1]

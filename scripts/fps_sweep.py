@@ -44,5 +44,29 @@ def main():
     os.environ.pop("PN2_FPS_CLUSTER"), os.environ.pop("PN2_FPS_THREADS")
 
 
+def profile():
+    from situation3d_b200._lib import check, lib, ptr, stream_ptr
+    B = 8
+    xyz = torch.from_numpy(np.stack([make_scene(s, 40000, 0)[:, :3] for s in range(B)])).cuda().contiguous()
+    print("phase profile (cycles/round of thread 0, CTA 0): update, warp argmax, exchange, scene argmax | wall us/round -> implied MHz")
+    for n, m in [(40000, 2048), (2048, 1024), (512, 256)]:
+        src = xyz[:, :n].contiguous()
+        idx = torch.empty((B, m), dtype=torch.int32, device="cuda")
+        prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            check(lib.pn2_debug_fps_profile(B, n, m, ptr(src), ptr(idx), ptr(prof), stream_ptr()), "prof")
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        check(lib.pn2_debug_fps_profile(B, n, m, ptr(src), ptr(idx), ptr(prof), stream_ptr()), "prof")
+        e.record()
+        e.synchronize()
+        us = 1e3 * s.elapsed_time(e) / (m - 1)
+        pc = prof.cpu().numpy()[:5] / (m - 1)
+        print("%d->%d: %s | %.3f us/round -> %.0f MHz" % (n, m, np.round(pc, 1), us, pc[:4].sum() / us))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "profile":
+        profile()
+    else:
+        main()

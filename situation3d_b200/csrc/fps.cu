@@ -113,16 +113,72 @@ __device__ __forceinline__ int unrank(uint32_t g, int lg_bs, int cnt, int n)
     return k < n ? (int)k : -1;
 }
 
-// P = point slots per thread.  REGS: xyz of the slots are kept in registers (P <= 16);
-// otherwise they are read back from this CTA's shared-memory copy each round.
-// CLUSTER: compiled-in switch between the single-CTA and the DSMEM exchange.
+// ---- packed fp32x2 arithmetic (sm_100): two IEEE round-to-nearest operations per instruction, so
+// the per-point results are bit-identical to the scalar FADD / FMUL / FFMA sequence of sqdist3.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct Cand {   // a candidate of the argmax: distance, slot offset inside the thread, coordinates
+    float v;
+    int i;
+    float x, y, z;
+};
+__device__ __forceinline__ void take_later_if_greater(Cand &a, const Cand &b)
+{
+    const bool g = b.v > a.v;   // strict: on ties the earlier slot stays
+    a.v = g ? b.v : a.v; a.i = g ? b.i : a.i; a.x = g ? b.x : a.x; a.y = g ? b.y : a.y; a.z = g ? b.z : a.z;
+}
+
+// P = point slots per thread (even).  REGS: xyz of the slots are kept in registers (P <= 16); otherwise
+// they are read back from this CTA's shared-memory copy each round.  CLUSTER: compiled-in switch
+// between the single-CTA exchange (shared memory + bar.sync) and the DSMEM exchange.
 template <int P, bool REGS, bool CLUSTER, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int *__restrict__ idxs,
-           float *__restrict__ new_xyz)
+           float *__restrict__ new_xyz, long long *__restrict__ prof)
 {
-    extern __shared__ float dyn[];   // sx[P*T], sy[P*T], sz[P*T]
-    // winners table, double buffered: (distance key, x, y, z) per warp of every CTA
+    static_assert(P % 2 == 0, "slots are processed in pairs");
+    extern __shared__ float dyn[];   // !REGS: sx[P*T], sy[P*T], sz[P*T]
+    // winners table, double buffered: (distance key, x, y, z) of every warp of every CTA.  Slot s
+    // (= cluster-wide warp number) lives at position (s % K) * 32 + s / K, so that lane l reads its
+    // K consecutive slots l*K .. l*K+K-1 at positions i*32 + l: conflict free, and "lowest lane"
+    // is "lowest slot".
     __shared__ __align__(16) uint4 table[2][kMaxCluster * kMaxWarps];
     __shared__ __align__(8) uint64_t bar[2];
 
@@ -135,29 +191,51 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
     float *sx = dyn, *sy = dyn + P * T, *sz = dyn + 2 * P * T;
     const uint32_t g0 = (rank * T + tid) * P;          // first slot of this thread
     const int entries = (int)C * W;                      // table entries per round
+    const int K = (entries + 31) >> 5;                   // entries per lane (1, 2, 4 or 8)
+    const int myslot = (int)rank * W + warp;
+    const uint32_t mypos = (uint32_t)((myslot % K) * 32 + myslot / K);
 
-    float px[P], py[P], pz[P], pt[P];
+    uint64_t px2[P / 2], py2[P / 2], pz2[P / 2];
+    float pt[P];
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const int k = unrank(g0 + i, lg_bs, cnt, n);
-        float x = 0.f, y = 0.f, z = 0.f, t = -1.f;   // -1: never a candidate (fminf keeps it at -1)
-        if (k >= 0) {
-            x = __ldg(p + 3 * (size_t)k);
-            y = __ldg(p + 3 * (size_t)k + 1);
-            z = __ldg(p + 3 * (size_t)k + 2);
-            // sampling_gpu.cu:100-101: float mag compared against the double literal 1e-3
-            if (!((double)sqnorm3(x, y, z) <= 1e-3)) t = 1e10f;   // sampling.cpp:74-76
+    for (int i = 0; i < P; i += 2) {
+        float c[2][3], t[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = unrank(g0 + i + h, lg_bs, cnt, n);
+            c[h][0] = c[h][1] = c[h][2] = 0.f;
+            t[h] = -1.f;                                 // -1: never a candidate (fminf keeps it at -1)
+            if (k >= 0) {
+                c[h][0] = __ldg(p + 3 * (size_t)k);
+                c[h][1] = __ldg(p + 3 * (size_t)k + 1);
+                c[h][2] = __ldg(p + 3 * (size_t)k + 2);
+                // sampling_gpu.cu:100-101: float mag compared against the double literal 1e-3
+                if (!((double)sqnorm3(c[h][0], c[h][1], c[h][2]) <= 1e-3)) t[h] = 1e10f;   // sampling.cpp:74-76
+            }
+            if (!REGS) { sx[(i + h) * T + tid] = c[h][0]; sy[(i + h) * T + tid] = c[h][1]; sz[(i + h) * T + tid] = c[h][2]; }
         }
-        px[i] = x; py[i] = y; pz[i] = z; pt[i] = t;
-        sx[i * T + tid] = x; sy[i * T + tid] = y; sz[i * T + tid] = z;
+        px2[i / 2] = pack2(c[0][0], c[1][0]); py2[i / 2] = pack2(c[0][1], c[1][1]); pz2[i / 2] = pack2(c[0][2], c[1][2]);
+        pt[i] = t[0]; pt[i + 1] = t[1];
     }
+    for (int i = tid; i < 2 * kMaxCluster * kMaxWarps; i += T) (&table[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    // addresses that do not change from round to round
+    const uint32_t tab0 = smem_u32(&table[0][0]), bar0 = smem_u32(&bar[0]);
+    constexpr uint32_t kTabBytes = kMaxCluster * kMaxWarps * 16;
+    uint32_t r_tab = 0, r_bar = 0;                       // lane c < C: this warp's entry / the barrier in CTA c
     if (CLUSTER) {
         if (tid == 0) {
-            mbar_init(smem_u32(&bar[0]), 1);
-            mbar_init(smem_u32(&bar[1]), 1);
+            mbar_init(bar0, 1);
+            mbar_init(bar0 + 8, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        if (lane < C) {
+            r_tab = map_to_cta(tab0 + mypos * 16, lane);
+            r_bar = map_to_cta(bar0, lane);
+        }
+        __syncthreads();
         cluster_sync_all();
+    } else {
+        __syncthreads();
     }
 
     // sampling_gpu.cu:85-87: the first sample is point 0, unconditionally
@@ -168,75 +246,112 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
         if (out_xyz) { out_xyz[0] = ox; out_xyz[1] = oy; out_xyz[2] = oz; }
     }
 
-    for (int j = 1; j < m; ++j) {
-        const int r = j - 1, buf = r & 1;
-        float best = -1.f;
-        int bi = 0;
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            float x, y, z;
-            if (REGS) { x = px[i]; y = py[i]; z = pz[i]; }
-            else { x = sx[i * T + tid]; y = sy[i * T + tid]; z = sz[i * T + tid]; }
-            const float d = sqdist3(x, y, z, ox, oy, oz);
-            const float d2 = fminf(d, pt[i]);
-            pt[i] = d2;
-            if (d2 > best) { best = d2; bi = i; }   // strict: earliest slot wins inside a thread
-        }
-        const uint32_t hi = best >= 0.f ? __float_as_uint(best) + 1u : 0u;
+    // optional phase profile (diagnostics): SM cycles of thread 0 of CTA 0 per phase, summed over rounds
+    long long pc[5] = {0, 0, 0, 0, 0}, tprev = 0;
+    const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
+    if (profiling) tprev = clock64();
+#define PN2_FPS_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
 
-        // warp winner: largest key, lowest lane among equals
+    for (int j = 1; j < m; ++j) {
+        const int r = j - 1;
+        const uint32_t boff = (uint32_t)(r & 1);
+        // ---- distance update: all slots independently, then a tournament (depth log2 P) ----
+        const uint64_t nx2 = pack2(-ox, -ox), ny2 = pack2(-oy, -oy), nz2 = pack2(-oz, -oz);
+        Cand cd[P];
+#pragma unroll
+        for (int i = 0; i < P; i += 2) {
+            uint64_t x2 = px2[i / 2], y2 = py2[i / 2], z2 = pz2[i / 2];
+            if (!REGS) {
+                x2 = pack2(sx[i * T + tid], sx[(i + 1) * T + tid]);
+                y2 = pack2(sy[i * T + tid], sy[(i + 1) * T + tid]);
+                z2 = pack2(sz[i * T + tid], sz[(i + 1) * T + tid]);
+            }
+            // (x - ox)^2 + (y - oy)^2 + (z - oz)^2 as FMUL, FFMA, FFMA with the x term first (sqdist3)
+            const uint64_t dx = add2(x2, nx2), dy = add2(y2, ny2), dz = add2(z2, nz2);
+            const uint64_t d = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float d0, d1;
+            unpack2(d, d0, d1);
+            pt[i] = fminf(d0, pt[i]);
+            pt[i + 1] = fminf(d1, pt[i + 1]);
+            cd[i].v = pt[i]; cd[i].i = i;
+            cd[i + 1].v = pt[i + 1]; cd[i + 1].i = i + 1;
+            if (REGS) {
+                unpack2(x2, cd[i].x, cd[i + 1].x);
+                unpack2(y2, cd[i].y, cd[i + 1].y);
+                unpack2(z2, cd[i].z, cd[i + 1].z);
+            } else {   // coordinates are fetched from shared memory after the tournament
+                cd[i].x = cd[i].y = cd[i].z = 0.f;
+                cd[i + 1].x = cd[i + 1].y = cd[i + 1].z = 0.f;
+            }
+        }
+#pragma unroll
+        for (int st = 1; st < P; st *= 2)
+#pragma unroll
+            for (int i = 0; i + st < P; i += 2 * st) take_later_if_greater(cd[i], cd[i + st]);
+        Cand best = cd[0];
+        if (!REGS) { best.x = sx[best.i * T + tid]; best.y = sy[best.i * T + tid]; best.z = sz[best.i * T + tid]; }
+        const uint32_t hi = best.v >= 0.f ? __float_as_uint(best.v) + 1u : 0u;
+        PN2_FPS_MARK(0)
+
+        // ---- warp winner: largest key, lowest lane among equals ----
         const uint32_t wmax = __reduce_max_sync(kFull, hi);
         const int wsrc = __ffs(__ballot_sync(kFull, hi == wmax)) - 1;
         const bool warp_owner = lane == wsrc;
+        PN2_FPS_MARK(1)
+        const uint32_t tab = tab0 + boff * kTabBytes;
         if (!CLUSTER) {
-            if (warp_owner) {
-                const int s = bi * T + tid;
-                table[buf][warp] = make_uint4(wmax, __float_as_uint(sx[s]), __float_as_uint(sy[s]),
-                                              __float_as_uint(sz[s]));
-            }
+            if (warp_owner)
+                sts128(tab + mypos * 16, make_uint4(wmax, __float_as_uint(best.x), __float_as_uint(best.y),
+                                                    __float_as_uint(best.z)));
             __syncthreads();
         } else {
             // every warp publishes its winner to all CTAs of the cluster (lane c -> CTA c)
-            const uint32_t mb = smem_u32(&bar[buf]);
-            const int s = bi * T + tid;
-            const uint32_t vx = __shfl_sync(kFull, __float_as_uint(sx[s]), wsrc);
-            const uint32_t vy = __shfl_sync(kFull, __float_as_uint(sy[s]), wsrc);
-            const uint32_t vz = __shfl_sync(kFull, __float_as_uint(sz[s]), wsrc);
-            if (lane < C)
-                st_async_v4(map_to_cta(smem_u32(&table[buf][rank * W + warp]), lane), wmax, vx, vy, vz,
-                            map_to_cta(mb, lane));
-            if (tid == 0) mbar_arrive_expect_tx(mb, 16u * entries);
-            mbar_wait(mb, (r >> 1) & 1);
+            const uint32_t vx = __shfl_sync(kFull, __float_as_uint(best.x), wsrc);
+            const uint32_t vy = __shfl_sync(kFull, __float_as_uint(best.y), wsrc);
+            const uint32_t vz = __shfl_sync(kFull, __float_as_uint(best.z), wsrc);
+            if (lane < C) st_async_v4(r_tab + boff * kTabBytes, wmax, vx, vy, vz, r_bar + boff * 8);
+            if (tid == 0) mbar_arrive_expect_tx(bar0 + boff * 8, 16u * entries);
+            mbar_wait(bar0 + boff * 8, (r >> 1) & 1);
         }
-        // winner of the whole scene: every warp reduces the same table (entries <= 256)
-        uint4 e = make_uint4(0u, 0u, 0u, 0u);
-        int eslot = lane;
-        for (int q = lane; q < entries; q += 32) {       // ascending slots: '>' keeps the earliest
-            const uint4 v = table[buf][q];
-            if (v.x > e.x) { e = v; eslot = q; }
-        }
-        const uint32_t smax = __reduce_max_sync(kFull, e.x);
-        // among lanes holding the maximum the smallest table slot wins (slot order = point order)
-        const uint32_t cand = e.x == smax ? (uint32_t)eslot : 0xffffu;
-        const uint32_t sslot = __reduce_min_sync(kFull, cand);
-        const int ssrc = __ffs(__ballot_sync(kFull, cand == sslot)) - 1;
-        const float nx = __uint_as_float(__shfl_sync(kFull, e.y, ssrc));
-        const float ny = __uint_as_float(__shfl_sync(kFull, e.z, ssrc));
-        const float nz = __uint_as_float(__shfl_sync(kFull, e.w, ssrc));
+        PN2_FPS_MARK(2)
+        // ---- winner of the whole scene: every warp reduces the same table ----
+        uint4 e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            e[i] = i < K ? lds128(tab + (uint32_t)(i * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
+        int ei[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ei[i] = i;
+#pragma unroll
+        for (int st = 1; st < 8; st *= 2)
+#pragma unroll
+            for (int i = 0; i + st < 8; i += 2 * st)
+                if (e[i + st].x > e[i].x) { e[i] = e[i + st]; ei[i] = ei[i + st]; }
+        const uint32_t smax = __reduce_max_sync(kFull, e[0].x);
+        const int ssrc = __ffs(__ballot_sync(kFull, e[0].x == smax)) - 1;   // lowest lane = lowest slot
+        const float nx = __uint_as_float(__shfl_sync(kFull, e[0].y, ssrc));
+        const float ny = __uint_as_float(__shfl_sync(kFull, e[0].z, ssrc));
+        const float nz = __uint_as_float(__shfl_sync(kFull, e[0].w, ssrc));
+        const int sslot = ssrc * K + __shfl_sync(kFull, ei[0], ssrc);
 
         const bool none = smax == 0u;   // every point skipped: the reference's reduction leaves besti = 0
         ox = none ? p0x : nx; oy = none ? p0y : ny; oz = none ? p0z : nz;
+        PN2_FPS_MARK(3)
         // the thread that owns the winning slot records it (off the critical path)
-        if (warp_owner && (int)sslot == (int)(rank * W + warp)) {
-            out_idx[j] = none ? (int)kNoSlot : (int)(g0 + bi);
+        if (warp_owner && sslot == myslot) {
+            out_idx[j] = none ? (int)kNoSlot : (int)(g0 + best.i);
             if (out_xyz) { out_xyz[3 * j] = ox; out_xyz[3 * j + 1] = oy; out_xyz[3 * j + 2] = oz; }
         }
     }
-    if (CLUSTER) cluster_sync_all();   // no CTA leaves while a peer may still address its shared memory
-    else __syncthreads();
+    if (profiling) {
+        PN2_FPS_MARK(4)
+        for (int i = 0; i < 5; ++i) prof[i] = pc[i];
+    }
+#undef PN2_FPS_MARK
     // slots -> point indices (the stores above were made by threads of this cluster)
     __threadfence();
-    if (CLUSTER) cluster_sync_all();
+    if (CLUSTER) cluster_sync_all();   // also: no CTA leaves while a peer may still address its shared memory
+    else __syncthreads();
     for (int j = rank * T + tid; j < m; j += C * T) {
         const uint32_t g = (uint32_t)out_idx[j];
         out_idx[j] = g == kNoSlot ? 0 : unrank(g, lg_bs, cnt, n);
@@ -255,7 +370,7 @@ static int ref_block_lg(int n)
     return lg;
 }
 
-static const int kPpt[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
+static const int kPpt[] = {2, 4, 6, 8, 10, 12, 16, 20, 24, 32};
 
 static bool make_plan(int n, FpsPlan *pl)
 {
@@ -293,10 +408,10 @@ static bool make_plan(int n, FpsPlan *pl)
 
 template <int P, bool REGS, int MAXT>
 static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
-                  cudaStream_t stream)
+                  long long *prof, cudaStream_t stream)
 {
     auto kern = pl.cluster > 1 ? fps_kernel<P, REGS, true, MAXT> : fps_kernel<P, REGS, false, MAXT>;
-    const size_t smem = (size_t)3 * P * pl.threads * sizeof(float);
+    const size_t smem = REGS ? 0 : (size_t)3 * P * pl.threads * sizeof(float);
     PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (pl.cluster > 8)
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -312,27 +427,25 @@ static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PN2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, n, m, pl.lg_bs, pl.cnt, xyz, idxs, new_xyz));
+    PN2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, n, m, pl.lg_bs, pl.cnt, xyz, idxs, new_xyz, prof));
     return PN2_OK;
 }
 
 static int dispatch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int *idxs,
-                    float *new_xyz, cudaStream_t s)
+                    float *new_xyz, long long *prof, cudaStream_t s)
 {
 #define PN2_FPS_CASE(P, REGS, MAXT) \
-    case P: return launch<P, REGS, MAXT>(pl, b, n, m, xyz, idxs, new_xyz, s)
+    case P: return launch<P, REGS, MAXT>(pl, b, n, m, xyz, idxs, new_xyz, prof, s)
     if (pl.threads <= 256) {
         switch (pl.ppt) {
-            PN2_FPS_CASE(1, true, 256); PN2_FPS_CASE(2, true, 256); PN2_FPS_CASE(3, true, 256);
-            PN2_FPS_CASE(4, true, 256); PN2_FPS_CASE(5, true, 256); PN2_FPS_CASE(6, true, 256);
+            PN2_FPS_CASE(2, true, 256); PN2_FPS_CASE(4, true, 256); PN2_FPS_CASE(6, true, 256);
             PN2_FPS_CASE(8, true, 256); PN2_FPS_CASE(10, true, 256); PN2_FPS_CASE(12, true, 256);
             PN2_FPS_CASE(16, true, 256); PN2_FPS_CASE(20, true, 256); PN2_FPS_CASE(24, true, 256);
             PN2_FPS_CASE(32, true, 256);
         }
     } else {
         switch (pl.ppt) {
-            PN2_FPS_CASE(1, true, 512); PN2_FPS_CASE(2, true, 512); PN2_FPS_CASE(3, true, 512);
-            PN2_FPS_CASE(4, true, 512); PN2_FPS_CASE(5, true, 512); PN2_FPS_CASE(6, true, 512);
+            PN2_FPS_CASE(2, true, 512); PN2_FPS_CASE(4, true, 512); PN2_FPS_CASE(6, true, 512);
             PN2_FPS_CASE(8, true, 512); PN2_FPS_CASE(10, true, 512); PN2_FPS_CASE(12, true, 512);
             PN2_FPS_CASE(16, true, 512); PN2_FPS_CASE(20, false, 512); PN2_FPS_CASE(24, false, 512);
             PN2_FPS_CASE(32, false, 512);
@@ -348,8 +461,8 @@ using namespace pn2;
 
 extern "C" size_t pn2_furthest_point_sampling_workspace_bytes(int, int, int) { return 0; }
 
-extern "C" int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *idxs,
-                                               float *new_xyz, pn2_stream_t stream)
+static int fps_entry(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz, long long *prof,
+                     pn2_stream_t stream)
 {
     if (b < 0 || n < 0 || m < 0) return PN2_ERR_INVALID_ARGUMENT;
     if (b == 0 || m == 0) return PN2_OK;
@@ -364,7 +477,22 @@ extern "C" int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float 
     if (!xyz) return PN2_ERR_INVALID_ARGUMENT;
     FpsPlan pl;
     if (!make_plan(n, &pl)) return PN2_ERR_INVALID_ARGUMENT;   // n > 16 CTAs x 512 threads x 32 slots
-    return dispatch(pl, b, n, m, xyz, idxs, new_xyz, as_stream(stream));
+    return dispatch(pl, b, n, m, xyz, idxs, new_xyz, prof, as_stream(stream));
+}
+
+extern "C" int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *idxs,
+                                               float *new_xyz, pn2_stream_t stream)
+{
+    return fps_entry(b, n, m, xyz, idxs, new_xyz, nullptr, stream);
+}
+
+// Diagnostic: same launch, and prof[0..4] (device, 5 x int64) receives the SM cycles thread 0 of CTA 0
+// spent in {distance update, warp argmax, exchange (barrier / DSMEM wait), scene argmax, -} summed over rounds.
+extern "C" int pn2_debug_fps_profile(int b, int n, int m, const float *xyz, int *idxs, long long *prof,
+                                     pn2_stream_t stream)
+{
+    if (!prof) return PN2_ERR_INVALID_ARGUMENT;
+    return fps_entry(b, n, m, xyz, idxs, nullptr, prof, stream);
 }
 
 extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, void *, size_t,

@@ -58,7 +58,7 @@ static bool make_desc(int nlayers, const int *dims, MlpDesc *d)
     return true;
 }
 
-static size_t act_smem_bytes(const MlpDesc &d) { return sizeof(float) * kRows * (size_t)(d.ld[0] + d.ld[1]); }
+static size_t act_smem_bytes(const MlpDesc &d, int rows = kRows) { return sizeof(float) * rows * (size_t)(d.ld[0] + d.ld[1]); }
 
 // image[w_off + k*cpad + c] = w[c*cin + k]   (transposed, zero padded);  image[b_off + c] = bias[c]
 __global__ void pack_layer_kernel(int cin, int cout, int kpad, int cpad, const float *__restrict__ w,
@@ -73,18 +73,22 @@ __global__ void pack_layer_kernel(int cin, int cout, int kpad, int cpad, const f
     if (i < cpad) bt[i] = (i < cout && bias) ? __ldg(bias + i) : 0.f;
 }
 
-// One layer over the 64-row tile: out[r][c] = act(bias[c] + sum_k in[r][k] * wt[k][c]).
-// 256 threads = 16 row groups (4 rows) x 16 channel groups (4 channels); channels are
-// covered in passes of 64.  A warp touches two row groups (broadcast LDS.128) and 16
-// consecutive float4 of one weight row (256 contiguous bytes through the read-only path).
+// One layer over an R-row tile: out[r][c] = act(bias[c] + sum_k in[r][k] * wt[k][c]).
+// 256 threads = R/4 row groups (4 rows) x 1024/R channel groups (4 channels); channels are covered
+// in passes of 4096/R.  R = 64: a warp touches two row groups (broadcast LDS.128) and 16 consecutive
+// float4 of one weight row; R = 16 (few rows, e.g. the FP layers: more CTAs, each streaming the
+// weights once): a warp shares its rows and reads 512 contiguous bytes of the weight row.
+template <int R>
 __device__ __forceinline__ void mlp_layer(const float *__restrict__ in, int ldin, int kpad,
                                           const float *__restrict__ wt, const float *__restrict__ bias,
                                           int cpad, float *__restrict__ out, int ldout, bool relu)
 {
-    const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    constexpr int CG = 1024 / R;                  // channel groups
+    const int tr = threadIdx.x / CG, tc = threadIdx.x % CG;
     const float *a0 = in + (tr * 4) * ldin;
-    for (int cb = 0; cb < cpad; cb += 64) {
+    for (int cb = 0; cb < cpad; cb += CG * 4) {
         const int c0 = cb + tc * 4;
+        if (c0 >= cpad) break;
         float acc[4][4];
         const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + c0));
 #pragma unroll
@@ -118,13 +122,14 @@ __device__ __forceinline__ void mlp_layer(const float *__restrict__ in, int ldin
 }
 
 // runs all layers; returns the buffer index (0/1) holding the last layer's output
+template <int R>
 __device__ __forceinline__ int run_mlp(const MlpDesc &d, const float *__restrict__ image, float *buf0,
                                        float *buf1)
 {
     for (int l = 0; l < d.nlayers; ++l) {
         __syncthreads();
         const bool odd = l & 1;
-        mlp_layer(odd ? buf1 : buf0, odd ? d.ld[1] : d.ld[0], d.kpad[l], image + d.w_off[l], image + d.b_off[l],
+        mlp_layer<R>(odd ? buf1 : buf0, odd ? d.ld[1] : d.ld[0], d.kpad[l], image + d.w_off[l], image + d.b_off[l],
                   d.cpad[l], odd ? buf0 : buf1, odd ? d.ld[0] : d.ld[1], true);
     }
     __syncthreads();
@@ -179,7 +184,7 @@ sa_forward_f32_kernel(MlpDesc d, int n, int npoint, int nsample, int c, int ld, 
                 for (int k = lane; k < d.kpad[0]; k += 32) dst[k] = 0.f;
             }
         }
-        const int ob = run_mlp(d, image, buf0, buf1);
+        const int ob = run_mlp<kRows>(d, image, buf0, buf1);
         const float *res = ob ? buf1 : buf0;
         const int ldr = d.ld[ob];
         // max over the samples of each centre (pointnet2_modules.py:259-262)
@@ -209,6 +214,7 @@ sa_forward_f32_kernel(MlpDesc d, int n, int npoint, int nsample, int c, int ld, 
 // known_rows (b, m, c_known) and skip_rows (b, n, c_skip) are channel-last; dist2/idx come from
 // pn2_three_nn.  Weights follow pointnet2_modules.py:399-402 (sqrt, 1/(d+1e-8), normalise) and
 // the interpolation is the reference's FMUL,FFMA,FFMA (interpolate_gpu.cu:90-99).
+template <int R>
 __global__ void __launch_bounds__(kMlpThreads)
 fp_forward_f32_kernel(MlpDesc d, int n, int m, int c_known, int c_skip, const float *__restrict__ dist2,
                       const int *__restrict__ idx, const float *__restrict__ known_rows,
@@ -216,14 +222,14 @@ fp_forward_f32_kernel(MlpDesc d, int n, int m, int c_known, int c_skip, const fl
                       float *__restrict__ out, float *__restrict__ out_rows, int tiles_per_scene)
 {
     extern __shared__ __align__(16) float act[];
-    float *buf0 = act, *buf1 = act + kRows * d.ld[0];
+    float *buf0 = act, *buf1 = act + R * d.ld[0];
     const int bi = blockIdx.x / tiles_per_scene;
-    const int row0 = (blockIdx.x % tiles_per_scene) * kRows;
-    const int rows = min(kRows, n - row0);
+    const int row0 = (blockIdx.x % tiles_per_scene) * R;
+    const int rows = min(R, n - row0);
     const int cout = d.dims[d.nlayers];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int r = warp; r < kRows; r += kMlpThreads / 32) {
+    for (int r = warp; r < R; r += kMlpThreads / 32) {
         float *dst = buf0 + r * d.ld[0];
         if (r < rows) {
             const size_t j = (size_t)bi * n + row0 + r;
@@ -252,12 +258,12 @@ fp_forward_f32_kernel(MlpDesc d, int n, int m, int c_known, int c_skip, const fl
             for (int k = lane; k < d.kpad[0]; k += 32) dst[k] = 0.f;
         }
     }
-    const int ob = run_mlp(d, image, buf0, buf1);
+    const int ob = run_mlp<R>(d, image, buf0, buf1);
     const float *res = ob ? buf1 : buf0;
     const int ldr = d.ld[ob];
     // out (b, cout, n): rows fastest so that stores coalesce; out_rows (b, n, cout): channels fastest
-    for (int t = threadIdx.x; t < cout * kRows; t += kMlpThreads) {
-        const int cc = t / kRows, r = t % kRows;
+    for (int t = threadIdx.x; t < cout * R; t += kMlpThreads) {
+        const int cc = t / R, r = t % R;
         if (r < rows) out[((size_t)bi * cout + cc) * n + row0 + r] = res[r * ldr + cc];
     }
     if (out_rows)
@@ -369,13 +375,24 @@ extern "C" int pn2_fp_forward_f32(int b, int n, int m, int c_known, int c_skip, 
     if (b == 0 || n == 0) return PN2_OK;
     if (!image || !out || (c_known > 0 && (!dist2 || !idx || !known_rows || m < 1)) || (c_skip > 0 && !skip_rows))
         return PN2_ERR_INVALID_ARGUMENT;
-    const size_t smem = act_smem_bytes(d);
-    if (smem > (size_t)kMaxSmem) return PN2_ERR_INVALID_ARGUMENT;
-    PN2_CUDA_TRY(cudaFuncSetAttribute(fp_forward_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    const int tiles = ceil_div(n, kRows);
-    fp_forward_f32_kernel<<<(unsigned)((long long)b * tiles), kMlpThreads, smem, as_stream(stream)>>>(
-        d, n, m, c_known, c_skip, dist2, idx, known_rows, skip_rows, static_cast<const float *>(image), out,
-        out_rows, tiles);
+    if (act_smem_bytes(d) > (size_t)kMaxSmem) return PN2_ERR_INVALID_ARGUMENT;
+    // few rows (the backbone's FP layers have 512 / 1024 points per scene): 16-row tiles give 4x the CTAs
+    const bool small = (long long)b * ceil_div(n, kRows) < 4 * kNumSMs;
+    if (small) {
+        const size_t smem = act_smem_bytes(d, 16);
+        PN2_CUDA_TRY(cudaFuncSetAttribute(fp_forward_f32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        const int tiles = ceil_div(n, 16);
+        fp_forward_f32_kernel<16><<<(unsigned)((long long)b * tiles), kMlpThreads, smem, as_stream(stream)>>>(
+            d, n, m, c_known, c_skip, dist2, idx, known_rows, skip_rows, static_cast<const float *>(image), out,
+            out_rows, tiles);
+    } else {
+        const size_t smem = act_smem_bytes(d);
+        PN2_CUDA_TRY(cudaFuncSetAttribute(fp_forward_f32_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        const int tiles = ceil_div(n, kRows);
+        fp_forward_f32_kernel<kRows><<<(unsigned)((long long)b * tiles), kMlpThreads, smem, as_stream(stream)>>>(
+            d, n, m, c_known, c_skip, dist2, idx, known_rows, skip_rows, static_cast<const float *>(image), out,
+            out_rows, tiles);
+    }
     PN2_LAUNCH_CHECK("fp_forward_f32");
     return PN2_OK;
 }

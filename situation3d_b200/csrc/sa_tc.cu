@@ -175,9 +175,10 @@ static bool make_shape(int c, int c1, int c2, int c3, SaTcShape *s)
     s->c = c; s->c1 = c1; s->c2 = c2; s->c3 = c3;
     s->row_elems = rup(c, 8);
     s->k0 = rup(s->row_elems + 8, 16);
-    s->w1_bytes = kop_bytes(c1, s->k0);
-    s->w2_bytes = kop_bytes(c2, c1);
-    s->w3_bytes = kop_bytes(c3, c2);
+    // image sections start on 1024-byte boundaries (128B-swizzle tiles need it)
+    s->w1_bytes = (uint32_t)rup((int)kop_bytes(c1, s->k0), 1024);
+    s->w2_bytes = (uint32_t)rup((int)kop_bytes(c2, c1), 1024);
+    s->w3_bytes = (uint32_t)rup((int)kop_bytes(c3, c2), 1024);
     s->bias_bytes = 4u * (c2 + c3);
     s->a0_bytes = kop_bytes(kTile, s->k0);
     s->a12_bytes = max(kop_bytes(kTile, c1), kop_bytes(kTile, c2));
@@ -293,6 +294,7 @@ __device__ __forceinline__ void store_act32(unsigned char *dst_base, int K, int 
 {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+        if (col0 + q * 8 >= K) break;     // widths that are a multiple of 16 but not of 32
         uint32_t w[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
