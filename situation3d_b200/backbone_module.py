@@ -49,7 +49,7 @@ class Pointnet2Backbone(nn.Module):
                                          mlp=[256, 128, 128, 256], **kw)
         self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
         self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
-        self._side_stream = None
+        self._side_streams = {}
 
     @staticmethod
     def _break_up_pc(pc):
@@ -77,9 +77,12 @@ class Pointnet2Backbone(nn.Module):
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
         xyz = pc[..., 0:3].contiguous()
         main = torch.cuda.current_stream(dev)
-        if self._side_stream is None or self._side_stream.device != dev:
-            self._side_stream = torch.cuda.Stream(device=dev)
-        side = self._side_stream
+        # one sampling stream per caller stream: callers that keep several batches in flight (one stream
+        # per batch) get independent sampling pyramids that overlap with each other's MLP kernels
+        key = (dev.index, main.cuda_stream)
+        side = self._side_streams.get(key)
+        if side is None:
+            side = self._side_streams[key] = torch.cuda.Stream(device=dev)
 
         # buffers are allocated on the main stream; the side stream only fills them
         inds = [torch.empty((B, m.npoint), dtype=torch.int32, device=dev) for m in sas]

@@ -154,15 +154,14 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-struct Cand {   // a candidate of the argmax: distance, slot offset inside the thread, coordinates
+struct Cand {   // a candidate of the argmax: distance and slot offset inside the thread
     float v;
     int i;
-    float x, y, z;
 };
 __device__ __forceinline__ void take_later_if_greater(Cand &a, const Cand &b)
 {
     const bool g = b.v > a.v;   // strict: on ties the earlier slot stays
-    a.v = g ? b.v : a.v; a.i = g ? b.i : a.i; a.x = g ? b.x : a.x; a.y = g ? b.y : a.y; a.z = g ? b.z : a.z;
+    a.v = g ? b.v : a.v; a.i = g ? b.i : a.i;
 }
 
 // P = point slots per thread (even).  REGS: xyz of the slots are kept in registers (P <= 16); otherwise
@@ -174,7 +173,7 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
            float *__restrict__ new_xyz, long long *__restrict__ prof)
 {
     static_assert(P % 2 == 0, "slots are processed in pairs");
-    extern __shared__ float dyn[];   // !REGS: sx[P*T], sy[P*T], sz[P*T]
+    extern __shared__ float dyn[];   // sx[P*T], sy[P*T], sz[P*T]: the winner's coordinates are fetched from here
     // winners table, double buffered: (distance key, x, y, z) of every warp of every CTA.  Slot s
     // (= cluster-wide warp number) lives at position (s % K) * 32 + s / K, so that lane l reads its
     // K consecutive slots l*K .. l*K+K-1 at positions i*32 + l: conflict free, and "lowest lane"
@@ -212,7 +211,7 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
                 // sampling_gpu.cu:100-101: float mag compared against the double literal 1e-3
                 if (!((double)sqnorm3(c[h][0], c[h][1], c[h][2]) <= 1e-3)) t[h] = 1e10f;   // sampling.cpp:74-76
             }
-            if (!REGS) { sx[(i + h) * T + tid] = c[h][0]; sy[(i + h) * T + tid] = c[h][1]; sz[(i + h) * T + tid] = c[h][2]; }
+            sx[(i + h) * T + tid] = c[h][0]; sy[(i + h) * T + tid] = c[h][1]; sz[(i + h) * T + tid] = c[h][2];
         }
         px2[i / 2] = pack2(c[0][0], c[1][0]); py2[i / 2] = pack2(c[0][1], c[1][1]); pz2[i / 2] = pack2(c[0][2], c[1][2]);
         pt[i] = t[0]; pt[i + 1] = t[1];
@@ -275,21 +274,14 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
             pt[i + 1] = fminf(d1, pt[i + 1]);
             cd[i].v = pt[i]; cd[i].i = i;
             cd[i + 1].v = pt[i + 1]; cd[i + 1].i = i + 1;
-            if (REGS) {
-                unpack2(x2, cd[i].x, cd[i + 1].x);
-                unpack2(y2, cd[i].y, cd[i + 1].y);
-                unpack2(z2, cd[i].z, cd[i + 1].z);
-            } else {   // coordinates are fetched from shared memory after the tournament
-                cd[i].x = cd[i].y = cd[i].z = 0.f;
-                cd[i + 1].x = cd[i + 1].y = cd[i + 1].z = 0.f;
-            }
         }
 #pragma unroll
         for (int st = 1; st < P; st *= 2)
 #pragma unroll
             for (int i = 0; i + st < P; i += 2 * st) take_later_if_greater(cd[i], cd[i + st]);
-        Cand best = cd[0];
-        if (!REGS) { best.x = sx[best.i * T + tid]; best.y = sy[best.i * T + tid]; best.z = sz[best.i * T + tid]; }
+        const Cand best = cd[0];
+        // the candidate's coordinates (3 LDS instead of carrying xyz through the tournament)
+        const float bx = sx[best.i * T + tid], by = sy[best.i * T + tid], bz = sz[best.i * T + tid];
         const uint32_t hi = best.v >= 0.f ? __float_as_uint(best.v) + 1u : 0u;
         PN2_FPS_MARK(0)
 
@@ -301,14 +293,13 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
         const uint32_t tab = tab0 + boff * kTabBytes;
         if (!CLUSTER) {
             if (warp_owner)
-                sts128(tab + mypos * 16, make_uint4(wmax, __float_as_uint(best.x), __float_as_uint(best.y),
-                                                    __float_as_uint(best.z)));
+                sts128(tab + mypos * 16, make_uint4(wmax, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz)));
             __syncthreads();
         } else {
             // every warp publishes its winner to all CTAs of the cluster (lane c -> CTA c)
-            const uint32_t vx = __shfl_sync(kFull, __float_as_uint(best.x), wsrc);
-            const uint32_t vy = __shfl_sync(kFull, __float_as_uint(best.y), wsrc);
-            const uint32_t vz = __shfl_sync(kFull, __float_as_uint(best.z), wsrc);
+            const uint32_t vx = __shfl_sync(kFull, __float_as_uint(bx), wsrc);
+            const uint32_t vy = __shfl_sync(kFull, __float_as_uint(by), wsrc);
+            const uint32_t vz = __shfl_sync(kFull, __float_as_uint(bz), wsrc);
             if (lane < C) st_async_v4(r_tab + boff * kTabBytes, wmax, vx, vy, vz, r_bar + boff * 8);
             if (tid == 0) mbar_arrive_expect_tx(bar0 + boff * 8, 16u * entries);
             mbar_wait(bar0 + boff * 8, (r >> 1) & 1);
@@ -411,7 +402,7 @@ static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int 
                   long long *prof, cudaStream_t stream)
 {
     auto kern = pl.cluster > 1 ? fps_kernel<P, REGS, true, MAXT> : fps_kernel<P, REGS, false, MAXT>;
-    const size_t smem = REGS ? 0 : (size_t)3 * P * pl.threads * sizeof(float);
+    const size_t smem = (size_t)3 * P * pl.threads * sizeof(float);
     PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (pl.cluster > 8)
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
