@@ -100,6 +100,15 @@ int pn2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out
 int pn2_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                    const float *xyz, int *idx, pn2_stream_t stream);
 
+/* Same result, bit for bit, through a uniform grid when the scene is large (n >= 4096): the points are
+ * binned into cells of edge >= 1.001*radius and each centre tests only the 27 surrounding cells; the
+ * ascending-index order of the reference is restored with a per-warp bitmap.  workspace:
+ * pn2_ball_query_workspace_bytes() bytes (0 for small scenes, then the plain scan runs). */
+size_t pn2_ball_query_workspace_bytes(int b, int n, int m, int nsample);
+int pn2_ball_query_ws(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                      const float *xyz, int *idx, void *workspace, size_t workspace_bytes,
+                      pn2_stream_t stream);
+
 /* points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample) */
 int pn2_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
                      const int *idx, float *out, pn2_stream_t stream);

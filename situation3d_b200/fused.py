@@ -140,13 +140,17 @@ def fps_into(xyz, inds, new_xyz):
                                                   stream_ptr()), "furthest_point_sampling_xyz")
 
 
-def ball_query(xyz, new_xyz, radius, nsample):
+def ball_query(xyz, new_xyz, radius, nsample, out=None):
+    """Ball query (uniform grid for large scenes, plain scan otherwise); the workspace comes from
+    PyTorch's caching allocator."""
     B, N, _ = xyz.shape
     m = new_xyz.shape[1]
-    idx = torch.empty((B, m, nsample), dtype=torch.int32, device=xyz.device)
+    idx = out if out is not None else torch.empty((B, m, nsample), dtype=torch.int32, device=xyz.device)
+    nbytes = lib.pn2_ball_query_workspace_bytes(B, N, m, int(nsample))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device) if nbytes else None
     with torch.cuda.device(xyz.device):
-        check(lib.pn2_ball_query(B, N, m, float(radius), int(nsample), ptr(new_xyz), ptr(xyz), ptr(idx),
-                                 stream_ptr()), "ball_query")
+        check(lib.pn2_ball_query_ws(B, N, m, float(radius), int(nsample), ptr(new_xyz), ptr(xyz), ptr(idx),
+                                    ptr(ws), nbytes, stream_ptr()), "ball_query")
     return idx
 
 

@@ -129,10 +129,8 @@ def ball_query(new_xyz, xyz, radius, nsample):
     B, m = new_xyz.size(0), new_xyz.size(1)
     N = xyz.size(1)
     idx = torch.zeros((B, m, nsample), device=new_xyz.device, dtype=torch.int32)
-    with torch.cuda.device(new_xyz.device):
-        check(lib.pn2_ball_query(B, N, m, float(radius), int(nsample), ptr(new_xyz), ptr(xyz), ptr(idx),
-                                 stream_ptr()), "ball_query")
-    return idx
+    from ..fused import ball_query as _ball_query      # workspace handling lives there
+    return _ball_query(xyz, new_xyz, radius, nsample, out=idx)
 
 
 def group_points(points, idx):

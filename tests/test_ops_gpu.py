@@ -113,6 +113,32 @@ def test_ball_query_vs_oracle(ext, b, n, m, r, ns):
     assert torch.equal(got, orc.ball_query(c, x, r, ns))
 
 
+@pytest.mark.parametrize("b,n,m,r,ns,scale", [
+    (2, 4096, 300, 0.3, 16, 1.0), (1, 5000, 64, 0.05, 8, 1.0), (2, 6000, 128, 2.5, 64, 1.0),
+    (1, 20000, 257, 0.15, 32, 3.0), (1, 4500, 40, 50.0, 128, 1.0), (1, 70000, 100, 0.2, 64, 2.0)])
+def test_ball_query_grid_path_vs_oracle(ext, b, n, m, r, ns, scale):
+    """n >= 4096 takes the uniform-grid kernel; results must equal the ascending scan bit for bit."""
+    x = cloud(700 + n, b, n, dup=n // 10, zeros=5, scale=scale)
+    c = torch.cat([x[:, : m // 2], cloud(800 + m, b, m - m // 2, scale=3.0 * scale)], dim=1).contiguous()
+    got = ext.ball_query(c.cuda(), x.cuda(), r, ns).cpu()
+    assert torch.equal(got, orc.ball_query(c, x, r, ns))
+
+
+def test_ball_query_grid_degenerate_geometry(ext):
+    g = torch.Generator().manual_seed(77)
+    # planar cloud (zero extent in z), a lattice with many points exactly on cell boundaries, NaN / inf points
+    plane = torch.rand(1, 5000, 3, generator=g) * 4
+    plane[..., 2] = 1.25
+    lattice = (torch.randint(0, 30, (1, 6000, 3), generator=g).float() * 0.2)
+    bad = torch.randn(1, 5000, 3, generator=g)
+    bad[0, 10] = float("nan")
+    bad[0, 11, 1] = float("inf")
+    for x, r in ((plane, 0.2), (lattice, 0.2), (lattice, 0.4), (bad, 0.3)):
+        c = torch.cat([x[:, :50], x[:, :50] + 0.05, torch.full((1, 3, 3), 100.0)], dim=1).contiguous()
+        got = ext.ball_query(c.cuda(), x.cuda(), r, 16).cpu()
+        assert torch.equal(got, orc.ball_query(c, x, r, 16))
+
+
 def test_ball_query_full_scene(ext):
     x = scene_xyz([2])
     inds = orc.furthest_point_sampling(x, 2048)
