@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--precision", default=None, help="fp32 | bf16 (default: bf16 when built, else fp32)")
     ap.add_argument("--batch", type=int, default=8, help="scenes per GPU per step")
     ap.add_argument("--points", type=int, default=40000)
-    ap.add_argument("--lanes", type=int, default=4,
+    ap.add_argument("--lanes", type=int, default=6,
                     help="batches in flight per GPU: step i runs on CUDA stream i %% lanes (1 = strictly serial steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")

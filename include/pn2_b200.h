@@ -191,6 +191,20 @@ int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, int c1, int 
                       float inv_radius, const float *xyz, const float *new_xyz, const void *table,
                       const int *idx, const void *weight_image, float *out, void *out_table,
                       pn2_stream_t stream);
+/* ---- fused feature-propagation layer on tcgen05 tensor cores ------------------------------------
+ * Same chain as pn2_fp_forward_f32 (3-NN weights -> three_interpolate -> cat(skip) -> 2-layer SharedMLP),
+ * inputs and outputs as bf16 channel-last rows: known_rows (b,m,c_known), skip_rows (b,n,c_skip),
+ * out (b,c2,n) f32, out_rows (b,n,c2) bf16 or NULL.  The weight image is built from the folded
+ * w1 (c1, c_known+c_skip) [interpolated channels first, as the reference concatenates], w2 (c2,c1).
+ * Supported: c_known, c_skip, c1 multiples of 64, c2 multiple of 16, c1,c2 <= 256. */
+int pn2_fp_tc_supported(int c_known, int c_skip, int c1, int c2);
+size_t pn2_fp_tc_weight_image_bytes(int c_known, int c_skip, int c1, int c2);
+int pn2_fp_tc_pack_weights(int c_known, int c_skip, int c1, int c2, const float *w1, const float *b1,
+                           const float *w2, const float *b2, void *image, pn2_stream_t stream);
+int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, int c1, int c2, const float *dist2,
+                      const int *idx, const void *known_rows, const void *skip_rows,
+                      const void *weight_image, float *out, void *out_rows, pn2_stream_t stream);
+
 /* Diagnostic: D (128 x n f32) = A (128 x k bf16) * B^T (n x k bf16) through the same shared-memory
  * layouts, descriptors and TMEM path as the fused kernel (one tile).  n, k multiples of 16. */
 int pn2_selftest_umma(int n, int k, const void *a, const void *b, float *d, pn2_stream_t stream);

@@ -65,12 +65,13 @@ class MlpImage:
                 self.key, self.image, self.dims, self.folded = key, None, None, None
                 return None
             dims = [folded[0][0].shape[1]] + [w.shape[0] for w, _ in folded]
-            self.image = _PACKERS[precision if kind == "sa" else "fp32"](dims, folded)
-            if self.image is None and precision == "bf16" and kind == "sa":
-                self.image = _pack_f32(dims, folded)      # shapes outside the tcgen05 kernel: fp32 kernel
+            packer = _PACKERS[precision] if kind == "sa" else (_pack_fp_bf16 if precision == "bf16" else _pack_f32)
+            self.image = packer(dims, folded)
+            if self.image is None and precision == "bf16":
+                self.image = _pack_f32(dims, folded)      # shapes outside the tcgen05 kernels: fp32 kernel
                 self.f32_only = True
             else:
-                self.f32_only = precision != "bf16" or kind != "sa"
+                self.f32_only = precision != "bf16"
             self.key, self.dims, self.folded = key, dims, folded
             self._f32_alt = None
         return self
@@ -106,6 +107,23 @@ def _pack_bf16(dims, folded):
     with torch.cuda.device(dev):
         check(lib.pn2_sa_tc_pack_weights(c, c1, c2, c3, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3),
                                          ptr(image), stream_ptr()), "sa_tc_pack_weights")
+    return image
+
+
+def _pack_fp_bf16(dims, folded):
+    """Weight image of the tcgen05 FP kernel (2 layers); None when the widths are outside its coverage."""
+    if len(folded) != 2:
+        return None
+    k0, c1, c2 = dims
+    nbytes = lib.pn2_fp_tc_weight_image_bytes(k0, 0, c1, c2)       # the image depends on c_known + c_skip only
+    if nbytes == 0:
+        return None
+    dev = folded[0][0].device
+    image = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    (w1, b1), (w2, b2) = folded
+    with torch.cuda.device(dev):
+        check(lib.pn2_fp_tc_pack_weights(k0, 0, c1, c2, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(image), stream_ptr()),
+              "fp_tc_pack_weights")
     return image
 
 
@@ -240,10 +258,34 @@ def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, w
     return out, out_rows
 
 
+def _bf16_rows(rows):
+    return rows if rows is None or rows.dtype == torch.bfloat16 else rows.bfloat16()
+
+
 def fp_forward_bf16(img, dist2, idx, known_rows, skip_rows, want_rows=True):
-    """FP layers of the bf16 configuration: the interpolation + MLP kernel itself is the fp32 one (the FP
-    stack is 5% of the backbone's FLOPs); only its inputs arrive as bf16 rows from the SA kernels."""
-    return fp_forward_f32(img, dist2, idx, _f32_rows(known_rows), _f32_rows(skip_rows), want_rows)
+    """Fused FP layer on tcgen05 (pn2_fp_tc_forward) over bf16 channel-last rows; widths the tensor-core
+    kernel does not cover run on the fp32 kernel."""
+    B, n, _ = idx.shape
+    m, c_known = known_rows.shape[1], known_rows.shape[2]
+    c_skip = 0 if skip_rows is None else skip_rows.shape[2]
+    dims = img.dims
+    ok = not img.f32_only and len(dims) == 3 and lib.pn2_fp_tc_supported(c_known, c_skip, dims[1], dims[2])
+    if not ok:
+        alt = img if img.f32_only else img._f32_alt
+        if alt is None:
+            alt = MlpImage()
+            alt.dims, alt.folded, alt.image = img.dims, img.folded, _pack_f32(img.dims, img.folded)
+            img._f32_alt = alt
+        return fp_forward_f32(alt, dist2, idx, _f32_rows(known_rows), _f32_rows(skip_rows), want_rows)
+    known_rows, skip_rows = _bf16_rows(known_rows).contiguous(), _bf16_rows(skip_rows)
+    cout = dims[2]
+    out = torch.empty((B, cout, n), dtype=torch.float32, device=idx.device)
+    out_rows = torch.empty((B, n, cout), dtype=torch.bfloat16, device=idx.device) if want_rows else None
+    with torch.cuda.device(idx.device):
+        check(lib.pn2_fp_tc_forward(B, n, m, c_known, c_skip, dims[1], dims[2], ptr(dist2), ptr(idx), ptr(known_rows),
+                                    ptr(skip_rows), ptr(img.image), ptr(out), ptr(out_rows), stream_ptr()),
+              "fp_tc_forward")
+    return out, out_rows
 
 
 SA_FORWARD = {"fp32": sa_forward_f32, "bf16": sa_forward_bf16}

@@ -93,3 +93,37 @@ def test_sa_tc_unsupported_shapes_use_fp32_kernel():
     with torch.no_grad():
         _, out, _ = mod.cuda()(xyz.cuda(), feats.cuda())
     torch.testing.assert_close(out.cpu(), want, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("n,m,ck,cs,mlp", [(300, 100, 256, 256, [512, 256, 256]), (1024, 512, 256, 256, [512, 256, 256]),
+                                            (129, 40, 64, 128, [192, 64, 48]), (70, 3, 128, 0, [128, 128, 16])])
+def test_fp_tc_vs_bf16_emulation(n, m, ck, cs, mlp):
+    """Tensor-core FP kernel against the reference wiring evaluated with the same rounding points:
+    bf16 inputs / weights / interpolated values / layer-1 activations, fp32 accumulation."""
+    from situation3d_b200 import fused
+    from situation3d_b200.pointnet2.pointnet2_modules import PointnetFPModule
+    from situation3d_b200.synthetic import randomize_bn_stats
+    torch.manual_seed(5)
+    mod = randomize_bn_stats(PointnetFPModule(mlp=list(mlp), precision="bf16")).eval()
+    g = torch.Generator().manual_seed(17)
+    unknown, known = torch.randn(2, n, 3, generator=g), torch.randn(2, m, 3, generator=g)
+    kf = _bf16(torch.randn(2, ck, m, generator=g).relu())
+    uf = _bf16(torch.randn(2, cs, n, generator=g).relu()) if cs else None
+    (w1, b1), (w2, b2) = fused.fold_shared_mlp(mod.mlp)
+    d2, idx = orc.three_nn(unknown, known)
+    recip = 1.0 / (torch.sqrt(d2) + 1e-8)
+    w = recip / recip.sum(dim=2, keepdim=True)
+    interp = _bf16(orc.three_interpolate(kf.contiguous(), idx, w))
+    x = torch.cat([interp, uf], dim=1) if cs else interp
+    h = _bf16(torch.relu(torch.einsum("oc,bcn->bon", _bf16(w1), x) + b1[None, :, None]))
+    want = torch.relu(torch.einsum("oc,bcn->bon", _bf16(w2), h) + b2[None, :, None])
+    mod = mod.cuda()
+    img = mod._image.get(mod.mlp, "bf16", kind="fp")
+    assert not img.f32_only
+    dd2, didx = fused.three_nn(unknown.cuda(), known.cuda())
+    known_rows = kf.transpose(1, 2).contiguous().bfloat16().cuda()
+    skip_rows = uf.transpose(1, 2).contiguous().bfloat16().cuda() if cs else None
+    out, out_rows = fused.fp_forward_bf16(img, dd2, didx, known_rows, skip_rows)
+    scale = float(want.abs().max())
+    assert float((out.cpu() - want).abs().max()) <= 6e-3 * scale
+    torch.testing.assert_close(out_rows.float().cpu().transpose(1, 2), out.cpu(), rtol=1e-2, atol=1e-2 * scale)
