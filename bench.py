@@ -334,7 +334,13 @@ def run_ours(args, rank, local_rank, world):
 
         for ln in lanes:
             ln.wait_stream(base)
-        run_steps(max(len(lanes), 2))                         # untimed: per-lane stream / allocator warm-up
+        run_steps(max(2 * len(lanes), W))                     # untimed: every lane twice, so that the caching
+        for ln in lanes:                                      # allocator owns both buffer sets a lane alternates
+            base.wait_stream(ln)                              # between (a cudaMalloc inside the timed region
+        torch.cuda.synchronize()                              # would serialise the device)
+        for ln in lanes:
+            ln.wait_stream(base)
+        run_steps(len(lanes))
         for ln in lanes:
             base.wait_stream(ln)
         barrier()
@@ -373,7 +379,7 @@ def run_ours(args, rank, local_rank, world):
         if not args.no_e2e:
             for ln in lanes:
                 ln.wait_stream(base)
-            e2e_loop(W)
+            e2e_loop(max(2 * len(lanes), W))
             for ln in lanes:
                 base.wait_stream(ln)
             barrier()
