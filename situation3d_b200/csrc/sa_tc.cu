@@ -29,6 +29,7 @@
 //
 // Precision: bf16 operands, fp32 accumulation (kind::f16); indices come from the fp32 kernels.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace pn2 {
 
@@ -367,6 +368,205 @@ sa_tc_kernel(const SaTcParams p)
     if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
+// ---- warp-specialised variant: gather warps run one tile ahead of the MMA / epilogue warps -----------
+// Same arithmetic as sa_tc_kernel.  The serial kernel above spends most of a tile waiting for the
+// gather (index load -> row addresses -> cp.async -> L2/HBM latency).  Here warps 4-7 only gather, into
+// a two-stage ring, and warps 0-3 only compute; a stage is handed over with mbarriers
+// (full: 128 producer arrivals after cp.async.wait_all + fence.proxy.async; empty: the tcgen05.commit
+// that follows the tile's last MMA).  Activations of layers 1 and 2 overwrite the stage the tile was
+// gathered into, so the ring needs no extra buffer.  Used when W1+W2+W3 and two stages fit in shared memory.
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr int kPipeThreads = 256;
+
+template <int NS, int TMEM_COLS>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+sa_tc_pipe_kernel(const SaTcParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const SaTcShape &s = p.s;
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const uint32_t resident = s.w1_bytes + s.w2_bytes + s.w3_bytes;
+    unsigned char *w1s = base, *w2s = base + s.w1_bytes, *w3s = base + s.w1_bytes + s.w2_bytes;
+    unsigned char *ring = base + resident;                                   // two stages of region_bytes
+    float *bias2 = reinterpret_cast<float *>(ring + 2 * s.region_bytes);
+    float *bias3 = bias2 + s.c2;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(bias3 + s.c3);            // full[2], empty[2], mma
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 5);
+    __shared__ int s_idx[2][kTile];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.image);
+        for (uint32_t i = tid; i < resident / 16; i += kPipeThreads) cp_async16(smem_u32(base) + i * 16, src + i);
+        const float *bsrc = reinterpret_cast<const float *>(p.image + resident);
+        for (int i = tid; i < s.c2 + s.c3; i += kPipeThreads) bias2[i] = __ldg(bsrc + i);
+        if (tid == 0) {
+            tc_mbar_init(smem_u32(mbar + 0), kTile);      // full[0]: every producer thread arrives
+            tc_mbar_init(smem_u32(mbar + 1), kTile);
+            tc_mbar_init(smem_u32(mbar + 2), 1);          // empty[0]: one tcgen05.commit
+            tc_mbar_init(smem_u32(mbar + 3), 1);
+            tc_mbar_init(smem_u32(mbar + 4), 1);          // MMA -> epilogue
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+        cp_async_wait_all();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = *tmem_slot;
+    const int nchunk = s.row_elems / 8, xchunk = nchunk, k0chunks = s.k0 / 8;
+
+    if (warp >= 4) {
+        // ===== gather warps =====
+        const int ptid = tid - kTile, pwarp = warp - 4;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int st = it & 1, u = it >> 1;
+            if (u > 0) tc_mbar_wait(smem_u32(mbar + 2 + st), (u - 1) & 1);     // the tile that used this stage is done
+            unsigned char *region = ring + st * s.region_bytes;
+            const uint32_t a_base = smem_u32(region);
+            const int bi = tile / p.tiles_per_scene;
+            const int row0 = (tile - bi * p.tiles_per_scene) * kTile;
+            const int centre0 = row0 / NS;
+            const int nb = __ldg(p.idx + (size_t)bi * p.npoint * NS + row0 + ptid);
+            s_idx[st][ptid] = nb;
+            named_bar_sync(2, kTile);
+            // feature rows first (long latency), then the xyz chunk of this thread's row
+            for (int r = pwarp; r < kTile; r += 4) {
+                const __nv_bfloat16 *src = p.table + ((size_t)bi * p.n + s_idx[st][r]) * s.row_elems;
+                for (int ch = lane; ch < nchunk; ch += 32)
+                    cp_async16(a_base + kop_chunk_off(kTile, s.k0, r, ch), src + ch * 8);
+            }
+            {
+                const float *pp = p.xyz + ((size_t)bi * p.n + nb) * 3;
+                const float *cc = p.new_xyz + ((size_t)bi * p.npoint + centre0 + ptid / NS) * 3;
+                float h[3], l[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float d = __fmul_rn(__fsub_rn(__ldg(pp + a), __ldg(cc + a)), p.inv_radius);
+                    h[a] = __bfloat162float(__float2bfloat16_rn(d));
+                    l[a] = d - h[a];
+                }
+                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, ptid, xchunk)) =
+                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], l[0]), pack_bf16(l[1], l[2]), pack_bf16(1.f, 1.f));
+                for (int ch = xchunk + 1; ch < k0chunks; ++ch)
+                    *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, ptid, ch)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            cp_async_wait_all();
+            fence_proxy_async();
+            tc_mbar_arrive(smem_u32(mbar + st));
+        }
+    } else {
+        // ===== MMA + epilogue warps =====
+        const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t w1_base = smem_u32(w1s), w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
+        const uint32_t idesc1 = umma_idesc(kTile, s.c1), idesc2 = umma_idesc(kTile, s.c2), idesc3 = umma_idesc(128, kTile);
+        const uint32_t mma_bar = smem_u32(mbar + 4);
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int st = it & 1, u = it >> 1;
+            unsigned char *region = ring + st * s.region_bytes;
+            const uint32_t a_base = smem_u32(region);
+            const int bi = tile / p.tiles_per_scene;
+            const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
+            tc_mbar_wait(smem_u32(mbar + st), u & 1);                          // gathered
+            tc_fence_after();
+            if (tid == 0) {
+                for (int ks = 0; ks < s.k0 / 16; ++ks)
+                    umma_bf16(tmem, kop_desc(a_base, kTile, s.k0, ks, 0), kop_desc(w1_base, s.c1, s.k0, ks, 0), idesc1, ks > 0);
+                umma_commit(mma_bar);
+            }
+            tc_mbar_wait(mma_bar, phase); phase ^= 1;
+            tc_fence_after();
+            for (int c0 = 0; c0 < s.c1; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(my_tmem + c0, v);
+                store_act32(region, s.c1, tid, c0, v, nullptr);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            named_bar_sync(1, kTile);
+            if (tid == 0) {
+                tc_fence_after();
+                for (int ks = 0; ks < s.c1 / 16; ++ks)
+                    umma_bf16(tmem, kop_desc(a_base, kTile, s.c1, ks, 0), kop_desc(w2_base, s.c2, s.c1, ks, 0), idesc2, ks > 0);
+                umma_commit(mma_bar);
+            }
+            tc_mbar_wait(mma_bar, phase); phase ^= 1;
+            tc_fence_after();
+            for (int c0 = 0; c0 < s.c2; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(my_tmem + c0, v);
+                store_act32(region, s.c2, tid, c0, v, bias2);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            named_bar_sync(1, kTile);
+            if (tid == 0) {
+                tc_fence_after();
+                for (int mt = 0; mt < s.c3 / 128; ++mt)
+                    for (int ks = 0; ks < s.c2 / 16; ++ks)
+                        umma_bf16(tmem + mt * kTile, kop_desc(w3_base, s.c3, s.c2, ks, mt * 128),
+                                  kop_desc(a_base, kTile, s.c2, ks, 0), idesc3, ks > 0);
+                umma_commit(mma_bar);
+                umma_commit(smem_u32(mbar + 2 + st));                           // stage free for the gather warps
+            }
+            tc_mbar_wait(mma_bar, phase); phase ^= 1;
+            tc_fence_after();
+            for (int mt = 0; mt < s.c3 / 128; ++mt) {
+                const int ch = mt * 128 + tid;
+                const float bias = bias3[ch];
+                float run = -3.0e38f;
+#pragma unroll
+                for (int q = 0; q < kTile / 32; ++q) {
+                    uint32_t v[32];
+                    tmem_ld32(my_tmem + mt * kTile + q * 32, v);
+                    if (NS >= 32) {
+                        float mx = __uint_as_float(v[0]);
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        run = fmaxf(run, mx);
+                        if (((q + 1) * 32) % NS == 0) {
+                            const int centre = centre0 + (q * 32) / NS;
+                            const float o = fmaxf(run + bias, 0.f);
+                            p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
+                            if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
+                            run = -3.0e38f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 32 / NS; ++g) {
+                            float mx = __uint_as_float(v[g * NS]);
+#pragma unroll
+                            for (int j = 1; j < NS; ++j) mx = fmaxf(mx, __uint_as_float(v[g * NS + j]));
+                            const int centre = centre0 + (q * 32) / NS + g;
+                            const float o = fmaxf(mx + bias, 0.f);
+                            p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
+                            if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(1, kTile);       // every epilogue warp is done with TMEM before the next tile's MMA
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
 // ---- a one-tile GEMM through the same helpers: D (128 x n) = A (128 x k) B^T (n x k) ---------------
 // Diagnostic entry point (tests/test_tc_gpu.py): isolates descriptor/layout errors from the fusion.
 __global__ void __launch_bounds__(kTcThreads)
@@ -422,6 +622,25 @@ static int launch_sa_tc(const SaTcParams &p, cudaStream_t stream)
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // warp-specialised two-stage variant when the resident weights and two gather stages fit
+    const uint32_t pipe_smem = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + 2u * p.s.region_bytes +
+                               p.s.bias_bytes + 128u;
+    const char *force = getenv("PN2_SA_TC_PIPE");
+    const bool want_pipe = force ? atoi(force) != 0 : true;
+    if (want_pipe && !p.s.w3_streamed && pipe_smem <= 227u * 1024u) {
+        const int grid = min(p.ntiles, sms);
+        if (p.s.tmem_cols == 128) {
+            auto kern = sa_tc_pipe_kernel<NS, 128>;
+            PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+            kern<<<grid, kPipeThreads, pipe_smem, stream>>>(p);
+        } else {
+            auto kern = sa_tc_pipe_kernel<NS, 256>;
+            PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+            kern<<<grid, kPipeThreads, pipe_smem, stream>>>(p);
+        }
+        PN2_LAUNCH_CHECK("sa_tc_forward(pipe)");
+        return PN2_OK;
+    }
     const int per_sm = max(1, min((int)((227u * 1024u) / (p.s.smem_bytes + 1024u)), 512 / p.s.tmem_cols));
     const int grid = min(p.ntiles, sms * per_sm);
     if (p.s.tmem_cols == 128) {
