@@ -176,16 +176,82 @@ __device__ __forceinline__ void store_act32(unsigned char *dst_base, int K, int 
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         if (col0 + q * 8 >= K) break;     // widths that are a multiple of 16 but not of 32
-        uint32_t w[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const int j = q * 8 + h * 2;
-            float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-            if (bias) { a += bias[col0 + j]; b += bias[col0 + j + 1]; }
-            w[h] = pack_bf16(fmaxf(a, 0.f), fmaxf(b, 0.f));
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (bias) {
+            b0 = *reinterpret_cast<const float4 *>(bias + col0 + q * 8);
+            b1 = *reinterpret_cast<const float4 *>(bias + col0 + q * 8 + 4);
         }
-        *reinterpret_cast<uint4 *>(dst_base + kop_chunk_off(kTile, K, row, (col0 >> 3) + q)) =
-            make_uint4(w[0], w[1], w[2], w[3]);
+        const int j = q * 8;
+        const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[j]) + b0.x, __uint_as_float(v[j + 1]) + b0.y);
+        const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[j + 2]) + b0.z, __uint_as_float(v[j + 3]) + b0.w);
+        const uint32_t w2 = pack_bf16_relu(__uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y);
+        const uint32_t w3 = pack_bf16_relu(__uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w);
+        *reinterpret_cast<uint4 *>(dst_base + kop_chunk_off(kTile, K, row, (col0 >> 3) + q)) = make_uint4(w0, w1, w2, w3);
+    }
+}
+
+// epilogue of layers 1 / 2 for columns [c_begin, c_end) of this thread's row: two TMEM loads in flight
+__device__ __forceinline__ void epilogue_act(uint32_t my_tmem, unsigned char *region, int K, int row, int c_begin,
+                                             int c_end, const float *bias)
+{
+    for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+        uint32_t va[32], vb[32];
+        const bool two = c0 + 32 < c_end;
+        tmem_ld32_issue(my_tmem + c0, va);
+        if (two) tmem_ld32_issue(my_tmem + c0 + 32, vb);
+        tmem_ld_wait();
+        store_act32(region, K, row, c0, va, bias);
+        if (two) store_act32(region, K, row, c0 + 32, vb, bias);
+    }
+}
+
+// layer-3 epilogue for sample columns [s_begin, s_end) (multiples of 32) of channel `ch`: max over each
+// centre's NS columns, then bias + ReLU (both commute with the max), fp32 (B,C3,npoint) + bf16 rows
+template <int NS>
+__device__ __forceinline__ void epilogue_pool(const SaTcParams &p, uint32_t taddr, int bi, int centre0, int ch,
+                                              float bias, int s_begin, int s_end)
+{
+    const int c3 = p.s.c3;
+    float run = -3.0e38f;
+    for (int q0 = s_begin; q0 < s_end; q0 += 64) {
+        uint32_t va[32], vb[32];
+        const bool two = q0 + 32 < s_end;
+        tmem_ld32_issue(taddr + q0, va);
+        if (two) tmem_ld32_issue(taddr + q0 + 32, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (half == 1 && !two) break;
+            const uint32_t(&v)[32] = half ? vb : va;
+            const int col = q0 + half * 32;
+            if (NS >= 32) {
+                float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+                for (int j = 4; j < 32; j += 2) {
+                    m0 = fmaxf(m0, __uint_as_float(v[j]));
+                    m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+                }
+                run = fmaxf(run, fmaxf(m0, m1));
+                if ((col + 32) % NS == 0) {
+                    const int centre = centre0 + col / NS;
+                    const float o = fmaxf(run + bias, 0.f);
+                    p.out[((size_t)bi * c3 + ch) * p.npoint + centre] = o;
+                    if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * c3 + ch] = __float2bfloat16_rn(o);
+                    run = -3.0e38f;
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 32 / NS; ++g) {
+                    float mx = __uint_as_float(v[g * NS]);
+#pragma unroll
+                    for (int j = 1; j < NS; ++j) mx = fmaxf(mx, __uint_as_float(v[g * NS + j]));
+                    const int centre = centre0 + col / NS + g;
+                    const float o = fmaxf(mx + bias, 0.f);
+                    p.out[((size_t)bi * c3 + ch) * p.npoint + centre] = o;
+                    if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * c3 + ch] = __float2bfloat16_rn(o);
+                }
+            }
+        }
     }
 }
 
@@ -287,11 +353,7 @@ sa_tc_kernel(const SaTcParams p)
             const uint4 *src = reinterpret_cast<const uint4 *>(p.image + s.w1_bytes + s.w2_bytes);
             for (uint32_t i = tid; i < s.w3_bytes / 16; i += kTcThreads) cp_async16(w3_base + i * 16, src + i);
         }
-        for (int c0 = 0; c0 < s.c1; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(my_tmem + c0, v);
-            store_act32(region, s.c1, tid, c0, v, nullptr);      // layer-1 bias went through the GEMM
-        }
+        epilogue_act(my_tmem, region, s.c1, tid, 0, s.c1, nullptr);      // layer-1 bias went through the GEMM
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
@@ -306,11 +368,7 @@ sa_tc_kernel(const SaTcParams p)
         tc_mbar_wait(smem_u32(mbar), phase);
         phase ^= 1;
         tc_fence_after();
-        for (int c0 = 0; c0 < s.c2; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(my_tmem + c0, v);
-            store_act32(region, s.c2, tid, c0, v, bias2);
-        }
+        epilogue_act(my_tmem, region, s.c2, tid, 0, s.c2, bias2);
         if (s.w3_streamed) cp_async_wait_all();
         tc_fence_before();
         fence_proxy_async();
@@ -328,40 +386,8 @@ sa_tc_kernel(const SaTcParams p)
         tc_mbar_wait(smem_u32(mbar), phase);
         phase ^= 1;
         tc_fence_after();
-        for (int mt = 0; mt < s.c3 / 128; ++mt) {
-            const int ch = mt * 128 + tid;
-            const float bias = bias3[ch];
-            float run = -3.0e38f;
-#pragma unroll
-            for (int q = 0; q < kTile / 32; ++q) {
-                uint32_t v[32];
-                tmem_ld32(my_tmem + mt * kTile + q * 32, v);
-                if (NS >= 32) {
-                    float m = __uint_as_float(v[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-                    run = fmaxf(run, m);
-                    if (((q + 1) * 32) % NS == 0) {
-                        const int centre = centre0 + (q * 32) / NS;
-                        const float o = fmaxf(run + bias, 0.f);      // bias and ReLU commute with the max
-                        p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
-                        if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
-                        run = -3.0e38f;
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 32 / NS; ++g) {
-                        float m = __uint_as_float(v[g * NS]);
-#pragma unroll
-                        for (int j = 1; j < NS; ++j) m = fmaxf(m, __uint_as_float(v[g * NS + j]));
-                        const int centre = centre0 + (q * 32) / NS + g;
-                        const float o = fmaxf(m + bias, 0.f);
-                        p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
-                        if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
-                    }
-                }
-            }
-        }
+        for (int mt = 0; mt < s.c3 / 128; ++mt)
+            epilogue_pool<NS>(p, my_tmem + mt * kTile, bi, centre0, mt * 128 + tid, bias3[mt * 128 + tid], 0, kTile);
         tc_fence_before();
         __syncthreads();      // TMEM and the activation region are reused by the next tile
     }
@@ -384,7 +410,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-constexpr int kPipeThreads = 256;
+constexpr int kPipeConsumers = 256;                 // warps 0-7: MMA issue + epilogues
+constexpr int kPipeProducers = 128;                 // warps 8-11: gather
+constexpr int kPipeThreads = kPipeConsumers + kPipeProducers;
 
 template <int NS, int TMEM_COLS>
 __global__ void __launch_bounds__(kPipeThreads, 1)
@@ -410,11 +438,11 @@ sa_tc_pipe_kernel(const SaTcParams p)
         const float *bsrc = reinterpret_cast<const float *>(p.image + resident);
         for (int i = tid; i < s.c2 + s.c3; i += kPipeThreads) bias2[i] = __ldg(bsrc + i);
         if (tid == 0) {
-            tc_mbar_init(smem_u32(mbar + 0), kTile);      // full[0]: every producer thread arrives
-            tc_mbar_init(smem_u32(mbar + 1), kTile);
-            tc_mbar_init(smem_u32(mbar + 2), 1);          // empty[0]: one tcgen05.commit
+            tc_mbar_init(smem_u32(mbar + 0), kPipeProducers);   // full[0]: every producer thread arrives
+            tc_mbar_init(smem_u32(mbar + 1), kPipeProducers);
+            tc_mbar_init(smem_u32(mbar + 2), 1);                // empty[0]: one tcgen05.commit
             tc_mbar_init(smem_u32(mbar + 3), 1);
-            tc_mbar_init(smem_u32(mbar + 4), 1);          // MMA -> epilogue
+            tc_mbar_init(smem_u32(mbar + 4), 1);                // MMA -> epilogue
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
@@ -427,9 +455,9 @@ sa_tc_pipe_kernel(const SaTcParams p)
     const uint32_t tmem = *tmem_slot;
     const int nchunk = s.row_elems / 8, xchunk = nchunk, k0chunks = s.k0 / 8;
 
-    if (warp >= 4) {
+    if (warp >= kPipeConsumers / 32) {
         // ===== gather warps =====
-        const int ptid = tid - kTile, pwarp = warp - 4;
+        const int ptid = tid - kPipeConsumers, pwarp = warp - kPipeConsumers / 32;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const int st = it & 1, u = it >> 1;
@@ -441,9 +469,9 @@ sa_tc_pipe_kernel(const SaTcParams p)
             const int centre0 = row0 / NS;
             const int nb = __ldg(p.idx + (size_t)bi * p.npoint * NS + row0 + ptid);
             s_idx[st][ptid] = nb;
-            named_bar_sync(2, kTile);
+            named_bar_sync(2, kPipeProducers);
             // feature rows first (long latency), then the xyz chunk of this thread's row
-            for (int r = pwarp; r < kTile; r += 4) {
+            for (int r = pwarp; r < kTile; r += kPipeProducers / 32) {
                 const __nv_bfloat16 *src = p.table + ((size_t)bi * p.n + s_idx[st][r]) * s.row_elems;
                 for (int ch = lane; ch < nchunk; ch += 32)
                     cp_async16(a_base + kop_chunk_off(kTile, s.k0, r, ch), src + ch * 8);
@@ -468,11 +496,19 @@ sa_tc_pipe_kernel(const SaTcParams p)
             tc_mbar_arrive(smem_u32(mbar + st));
         }
     } else {
-        // ===== MMA + epilogue warps =====
-        const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+        // ===== MMA + epilogue warps: warp w works on TMEM lanes 32*(w%4).. and on column half w/4 =====
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;                                    // TMEM lane = sample row / channel
+        const uint32_t my_tmem = tmem + ((uint32_t)(quarter * 32) << 16);
         const uint32_t w1_base = smem_u32(w1s), w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
         const uint32_t idesc1 = umma_idesc(kTile, s.c1), idesc2 = umma_idesc(kTile, s.c2), idesc3 = umma_idesc(128, kTile);
         const uint32_t mma_bar = smem_u32(mbar + 4);
+        // column ranges of this warp's half (multiples of 32)
+        const int h1 = ((s.c1 / 2 + 31) / 32) * 32, h2 = ((s.c2 / 2 + 31) / 32) * 32;
+        const int c1_lo = half ? h1 : 0, c1_hi = half ? s.c1 : min(h1, s.c1);
+        const int c2_lo = half ? h2 : 0, c2_hi = half ? s.c2 : min(h2, s.c2);
+        // layer 3: the 128 sample columns split at 64 when a centre's samples do not straddle the split
+        const int s_lo = NS <= 64 ? half * 64 : 0, s_hi = NS <= 64 ? half * 64 + 64 : (half ? 0 : kTile);
         uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -490,14 +526,10 @@ sa_tc_pipe_kernel(const SaTcParams p)
             }
             tc_mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
-            for (int c0 = 0; c0 < s.c1; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(my_tmem + c0, v);
-                store_act32(region, s.c1, tid, c0, v, nullptr);
-            }
+            epilogue_act(my_tmem, region, s.c1, row, c1_lo, c1_hi, nullptr);
             tc_fence_before();
             fence_proxy_async();
-            named_bar_sync(1, kTile);
+            named_bar_sync(1, kPipeConsumers);
             if (tid == 0) {
                 tc_fence_after();
                 for (int ks = 0; ks < s.c1 / 16; ++ks)
@@ -506,14 +538,10 @@ sa_tc_pipe_kernel(const SaTcParams p)
             }
             tc_mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
-            for (int c0 = 0; c0 < s.c2; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(my_tmem + c0, v);
-                store_act32(region, s.c2, tid, c0, v, bias2);
-            }
+            epilogue_act(my_tmem, region, s.c2, row, c2_lo, c2_hi, bias2);
             tc_fence_before();
             fence_proxy_async();
-            named_bar_sync(1, kTile);
+            named_bar_sync(1, kPipeConsumers);
             if (tid == 0) {
                 tc_fence_after();
                 for (int mt = 0; mt < s.c3 / 128; ++mt)
@@ -525,42 +553,11 @@ sa_tc_pipe_kernel(const SaTcParams p)
             }
             tc_mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
-            for (int mt = 0; mt < s.c3 / 128; ++mt) {
-                const int ch = mt * 128 + tid;
-                const float bias = bias3[ch];
-                float run = -3.0e38f;
-#pragma unroll
-                for (int q = 0; q < kTile / 32; ++q) {
-                    uint32_t v[32];
-                    tmem_ld32(my_tmem + mt * kTile + q * 32, v);
-                    if (NS >= 32) {
-                        float mx = __uint_as_float(v[0]);
-#pragma unroll
-                        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                        run = fmaxf(run, mx);
-                        if (((q + 1) * 32) % NS == 0) {
-                            const int centre = centre0 + (q * 32) / NS;
-                            const float o = fmaxf(run + bias, 0.f);
-                            p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
-                            if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
-                            run = -3.0e38f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 32 / NS; ++g) {
-                            float mx = __uint_as_float(v[g * NS]);
-#pragma unroll
-                            for (int j = 1; j < NS; ++j) mx = fmaxf(mx, __uint_as_float(v[g * NS + j]));
-                            const int centre = centre0 + (q * 32) / NS + g;
-                            const float o = fmaxf(mx + bias, 0.f);
-                            p.out[((size_t)bi * s.c3 + ch) * p.npoint + centre] = o;
-                            if (p.out_table) p.out_table[((size_t)bi * p.npoint + centre) * s.c3 + ch] = __float2bfloat16_rn(o);
-                        }
-                    }
-                }
-            }
+            if (s_lo < s_hi)
+                for (int mt = 0; mt < s.c3 / 128; ++mt)
+                    epilogue_pool<NS>(p, my_tmem + mt * kTile, bi, centre0, mt * 128 + row, bias3[mt * 128 + row], s_lo, s_hi);
             tc_fence_before();
-            named_bar_sync(1, kTile);       // every epilogue warp is done with TMEM before the next tile's MMA
+            named_bar_sync(1, kPipeConsumers);   // every epilogue warp is done with TMEM before the next tile's MMA
         }
     }
     __syncthreads();

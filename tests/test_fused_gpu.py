@@ -280,3 +280,40 @@ def test_reencode_roundtrip_property():
     _, fwd, _ = reencode_tokens(tok, pos, sit, w1, b1, w2, b2, want_prior=False)
     _, back, _ = reencode_tokens(tok, fwd, sit, w1, b1, w2, b2, to_agent_frame=True, want_prior=False)
     torch.testing.assert_close(back, pos, rtol=1e-4, atol=1e-4)
+
+
+def test_situated_scene_encoder_config3():
+    """BASELINE.json config 3: backbone + agent-frame transform + positional embedding of 256 visual tokens."""
+    from situation3d_b200.scene_encoder import SituatedSceneEncoder
+    from situation3d_b200.synthetic import make_batch, make_situations, randomize_bn_stats
+    torch.manual_seed(0)
+    enc = randomize_bn_stats(SituatedSceneEncoder(129, 256, precision="fp32")).eval()
+    pc = torch.from_numpy(make_batch(2, 40000, 129, first_seed=30))
+    sit = torch.from_numpy(make_situations(2, seed=1))
+    sd = {k[len("backbone_net."):]: v.clone() for k, v in enc.state_dict().items() if k.startswith("backbone_net.")}
+    want = orc.backbone(pc, sd)
+    tokens = want["fp2_features"][:, :, :256].transpose(1, 2).contiguous()
+    pos = want["fp2_xyz"][:, :256].contiguous()
+    pe = enc.reencoder.pos_embed
+    want_tok, want_pos, want_prior = orc.reencode(tokens, pos, sit, pe[0].weight.detach(), pe[0].bias.detach(),
+                                                  pe[2].weight.detach(), pe[2].bias.detach())
+    enc = enc.cuda()
+    with torch.no_grad():
+        d = enc({"point_clouds": pc.cuda(), "auxiliary_task": sit.cuda()})
+    assert torch.equal(d["scene_token_inds"].cpu(), want["sa1_inds"][:, :256])
+    assert torch.equal(d["scene_positions"].cpu(), pos)
+    assert_features(d["scene_feat"], want_tok, "fp32")
+    torch.testing.assert_close(d["scene_positions_agent"].cpu(), want_pos, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(d["auxiliary_task_loc_gt"].cpu(), want_prior, rtol=1e-3, atol=1e-7)
+
+
+def test_backbone_stress_config5_shape():
+    """BASELINE.json config 5 shape: 100k-point scene, SA1 npoint 4096 / nsample 64 (FPS on 16 CTAs with
+    shared-memory-resident coordinates, grid ball query, tensor-core SA) against the oracle."""
+    npoints = (4096, 2048, 1024, 512)
+    net, pc, sd, layers = _backbone_pair("bf16", 100000, npoints, seed=40, batch=1)
+    want = orc.backbone(pc, sd, layers)
+    with torch.no_grad():
+        out = net.cuda()({"point_clouds": pc.cuda()})
+    _check_backbone(out, want, "bf16")
+    assert out["fp2_features"].shape == (1, 256, 2048)
