@@ -160,6 +160,7 @@ __global__ void pack_weights_kernel(SaTcShape s, const float *__restrict__ w1, c
 struct SaTcParams {
     SaTcShape s;
     int n, npoint, tiles_per_scene, ntiles;
+    int nstage;             // gather ring depth of the warp-specialised kernel (2..4)
     float inv_radius;
     const float *xyz, *new_xyz;
     const __nv_bfloat16 *table;
@@ -413,6 +414,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 constexpr int kPipeConsumers = 256;                 // warps 0-7: MMA issue + epilogues
 constexpr int kPipeProducers = 128;                 // warps 8-11: gather
 constexpr int kPipeThreads = kPipeConsumers + kPipeProducers;
+constexpr int kMaxStages = 4;
 
 template <int NS, int TMEM_COLS>
 __global__ void __launch_bounds__(kPipeThreads, 1)
@@ -424,12 +426,13 @@ sa_tc_pipe_kernel(const SaTcParams p)
     unsigned char *base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     const uint32_t resident = s.w1_bytes + s.w2_bytes + s.w3_bytes;
     unsigned char *w1s = base, *w2s = base + s.w1_bytes, *w3s = base + s.w1_bytes + s.w2_bytes;
-    unsigned char *ring = base + resident;                                   // two stages of region_bytes
-    float *bias2 = reinterpret_cast<float *>(ring + 2 * s.region_bytes);
+    unsigned char *ring = base + resident;                                   // nstage stages of region_bytes
+    float *bias2 = reinterpret_cast<float *>(ring + p.nstage * s.region_bytes);
     float *bias3 = bias2 + s.c2;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(bias3 + s.c3);            // full[2], empty[2], mma
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 5);
-    __shared__ int s_idx[2][kTile];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(bias3 + s.c3);            // full[4], empty[4], mma
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 9);
+    __shared__ int s_idx[kMaxStages][kTile];
+    const int nstage = p.nstage;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {
@@ -438,11 +441,12 @@ sa_tc_pipe_kernel(const SaTcParams p)
         const float *bsrc = reinterpret_cast<const float *>(p.image + resident);
         for (int i = tid; i < s.c2 + s.c3; i += kPipeThreads) bias2[i] = __ldg(bsrc + i);
         if (tid == 0) {
-            tc_mbar_init(smem_u32(mbar + 0), kPipeProducers);   // full[0]: every producer thread arrives
-            tc_mbar_init(smem_u32(mbar + 1), kPipeProducers);
-            tc_mbar_init(smem_u32(mbar + 2), 1);                // empty[0]: one tcgen05.commit
-            tc_mbar_init(smem_u32(mbar + 3), 1);
-            tc_mbar_init(smem_u32(mbar + 4), 1);                // MMA -> epilogue
+            for (int i = 0; i < kMaxStages; ++i) {
+                // full: per producer thread one arrival when its cp.asyncs have landed + one explicit (release)
+                tc_mbar_init(smem_u32(mbar + i), 2 * kPipeProducers);
+                tc_mbar_init(smem_u32(mbar + kMaxStages + i), 1);   // empty: one tcgen05.commit
+            }
+            tc_mbar_init(smem_u32(mbar + 2 * kMaxStages), 1);       // MMA -> epilogue
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
@@ -459,23 +463,38 @@ sa_tc_pipe_kernel(const SaTcParams p)
         // ===== gather warps =====
         const int ptid = tid - kPipeConsumers, pwarp = warp - kPipeConsumers / 32;
         int it = 0;
+        // the neighbour index of this thread's row is fetched one tile ahead
+        int nb_next = 0;
+        if ((int)blockIdx.x < p.ntiles) {
+            const int bi0 = blockIdx.x / p.tiles_per_scene;
+            nb_next = __ldg(p.idx + (size_t)bi0 * p.npoint * NS + (blockIdx.x - bi0 * p.tiles_per_scene) * kTile + ptid);
+        }
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            const int st = it & 1, u = it >> 1;
-            if (u > 0) tc_mbar_wait(smem_u32(mbar + 2 + st), (u - 1) & 1);     // the tile that used this stage is done
+            const int st = it % nstage, u = it / nstage;
+            const int nb = nb_next;
+            {
+                const int nt = tile + gridDim.x;
+                if (nt < p.ntiles) {
+                    const int bn = nt / p.tiles_per_scene;
+                    nb_next = __ldg(p.idx + (size_t)bn * p.npoint * NS + (nt - bn * p.tiles_per_scene) * kTile + ptid);
+                }
+            }
+            if (u > 0) tc_mbar_wait(smem_u32(mbar + kMaxStages + st), (u - 1) & 1);   // the tile that used this stage is done
             unsigned char *region = ring + st * s.region_bytes;
             const uint32_t a_base = smem_u32(region);
             const int bi = tile / p.tiles_per_scene;
             const int row0 = (tile - bi * p.tiles_per_scene) * kTile;
             const int centre0 = row0 / NS;
-            const int nb = __ldg(p.idx + (size_t)bi * p.npoint * NS + row0 + ptid);
             s_idx[st][ptid] = nb;
             named_bar_sync(2, kPipeProducers);
-            // feature rows first (long latency), then the xyz chunk of this thread's row
+            // feature rows: no wait here -- the stage's "full" barrier is armed to fire when the copies land,
+            // so the gather warps run up to nstage tiles ahead of the tensor core
             for (int r = pwarp; r < kTile; r += kPipeProducers / 32) {
                 const __nv_bfloat16 *src = p.table + ((size_t)bi * p.n + s_idx[st][r]) * s.row_elems;
                 for (int ch = lane; ch < nchunk; ch += 32)
                     cp_async16(a_base + kop_chunk_off(kTile, s.k0, r, ch), src + ch * 8);
             }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar + st)) : "memory");
             {
                 const float *pp = p.xyz + ((size_t)bi * p.n + nb) * 3;
                 const float *cc = p.new_xyz + ((size_t)bi * p.npoint + centre0 + ptid / NS) * 3;
@@ -491,10 +510,10 @@ sa_tc_pipe_kernel(const SaTcParams p)
                 for (int ch = xchunk + 1; ch < k0chunks; ++ch)
                     *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, ptid, ch)) = make_uint4(0u, 0u, 0u, 0u);
             }
-            cp_async_wait_all();
             fence_proxy_async();
-            tc_mbar_arrive(smem_u32(mbar + st));
+            tc_mbar_arrive(smem_u32(mbar + st));                                   // release of the xyz chunk
         }
+        cp_async_wait_all();
     } else {
         // ===== MMA + epilogue warps: warp w works on TMEM lanes 32*(w%4).. and on column half w/4 =====
         const int quarter = warp & 3, half = warp >> 2;
@@ -502,7 +521,7 @@ sa_tc_pipe_kernel(const SaTcParams p)
         const uint32_t my_tmem = tmem + ((uint32_t)(quarter * 32) << 16);
         const uint32_t w1_base = smem_u32(w1s), w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
         const uint32_t idesc1 = umma_idesc(kTile, s.c1), idesc2 = umma_idesc(kTile, s.c2), idesc3 = umma_idesc(128, kTile);
-        const uint32_t mma_bar = smem_u32(mbar + 4);
+        const uint32_t mma_bar = smem_u32(mbar + 2 * kMaxStages);
         // column ranges of this warp's half (multiples of 32)
         const int h1 = ((s.c1 / 2 + 31) / 32) * 32, h2 = ((s.c2 / 2 + 31) / 32) * 32;
         const int c1_lo = half ? h1 : 0, c1_hi = half ? s.c1 : min(h1, s.c1);
@@ -512,12 +531,13 @@ sa_tc_pipe_kernel(const SaTcParams p)
         uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            const int st = it & 1, u = it >> 1;
+            const int st = it % nstage, u = it / nstage;
             unsigned char *region = ring + st * s.region_bytes;
             const uint32_t a_base = smem_u32(region);
             const int bi = tile / p.tiles_per_scene;
             const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
             tc_mbar_wait(smem_u32(mbar + st), u & 1);                          // gathered
+            fence_proxy_async();          // the gather's cp.async / st.shared writes -> visible to the tensor core
             tc_fence_after();
             if (tid == 0) {
                 for (int ks = 0; ks < s.k0 / 16; ++ks)
@@ -549,7 +569,7 @@ sa_tc_pipe_kernel(const SaTcParams p)
                         umma_bf16(tmem + mt * kTile, kop_desc(w3_base, s.c3, s.c2, ks, mt * 128),
                                   kop_desc(a_base, kTile, s.c2, ks, 0), idesc3, ks > 0);
                 umma_commit(mma_bar);
-                umma_commit(smem_u32(mbar + 2 + st));                           // stage free for the gather warps
+                umma_commit(smem_u32(mbar + kMaxStages + st));                  // stage free for the gather warps
             }
             tc_mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
@@ -614,17 +634,24 @@ umma_selftest_kernel(int n, int k, const __nv_bfloat16 *__restrict__ a, const __
 }
 
 template <int NS>
-static int launch_sa_tc(const SaTcParams &p, cudaStream_t stream)
+static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
 {
+    const SaTcParams &p = p_in;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // warp-specialised two-stage variant when the resident weights and two gather stages fit
-    const uint32_t pipe_smem = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + 2u * p.s.region_bytes +
-                               p.s.bias_bytes + 128u;
+    const uint32_t pipe_fixed = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + p.s.bias_bytes + 128u;
+    const uint32_t budget = 226u * 1024u;
+    int nstage = pipe_fixed < budget ? (int)((budget - pipe_fixed) / p.s.region_bytes) : 0;
+    nstage = min(nstage, kMaxStages);
+    if (const char *e = getenv("PN2_SA_TC_STAGES")) nstage = min(nstage, atoi(e));
+    const uint32_t pipe_smem = pipe_fixed + (uint32_t)max(nstage, 0) * p.s.region_bytes;
     const char *force = getenv("PN2_SA_TC_PIPE");
     const bool want_pipe = force ? atoi(force) != 0 : true;
-    if (want_pipe && !p.s.w3_streamed && pipe_smem <= 227u * 1024u) {
+    if (want_pipe && !p.s.w3_streamed && nstage >= 2) {
+        SaTcParams p = p_in;
+        p.nstage = nstage;
         const int grid = min(p.ntiles, sms);
         if (p.s.tmem_cols == 128) {
             auto kern = sa_tc_pipe_kernel<NS, 128>;
@@ -737,6 +764,7 @@ extern "C" int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, i
     p.image = static_cast<const unsigned char *>(weight_image);
     p.out = out;
     p.out_table = static_cast<__nv_bfloat16 *>(out_table);
+    p.nstage = 0;
     switch (nsample) {
     case 16: return launch_sa_tc<16>(p, as_stream(stream));
     case 32: return launch_sa_tc<32>(p, as_stream(stream));
