@@ -205,6 +205,10 @@ int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, int c1, int 
                       const int *idx, const void *known_rows, const void *skip_rows,
                       const void *weight_image, float *out, void *out_rows, pn2_stream_t stream);
 
+/* Diagnostic: while prof (device, 16 x int64) is non-NULL, the warp-specialised pn2_sa_tc_forward kernel
+ * records the SM cycles CTA 0 spends per phase ([0..6] MMA/epilogue warps, [7] tiles, [8..10] gather warps). */
+int pn2_debug_sa_tc_profile(long long *prof);
+
 /* Diagnostic: D (128 x n f32) = A (128 x k bf16) * B^T (n x k bf16) through the same shared-memory
  * layouts, descriptors and TMEM path as the fused kernel (one tile).  n, k multiples of 16. */
 int pn2_selftest_umma(int n, int k, const void *a, const void *b, float *d, pn2_stream_t stream);

@@ -68,6 +68,7 @@ _PROTOTYPES = {
     "pn2_fp_tc_weight_image_bytes": (c_size_t, [_i, _i, _i, _i]),
     "pn2_fp_tc_pack_weights": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "pn2_fp_tc_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_debug_sa_tc_profile": (_i, [_p]),
     "pn2_selftest_umma": (_i, [_i, _i, _p, _p, _p, _p]),
     "pn2_quaternions_to_rotation_matrices": (_i, [_i, _p, _p, _p]),
     "pn2_rotation_vectors_to_matrices": (_i, [_i, _p, _p, _p]),

@@ -215,23 +215,22 @@ fp_tc_kernel(const FpTcParams p)
             cp_async_wait_all();
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
+                const uint32_t elected = elect_one();
                 const uint32_t wb = smem_u32(stage_w);
-                if (!layer2) {
-                    const uint32_t ab = smem_u32(stage_a);
+                const int k2 = kb - nslab1;
+                // A: this stage's 64-column slab (layer 1) or slab k2 of the layer-1 activations (layer 2)
+                const uint64_t da = smem_desc(layer2 ? smem_u32(a1) + (uint32_t)k2 * (kFpTile * 128u) : smem_u32(stage_a),
+                                              1024u, kSw128);
+                const uint64_t db = smem_desc(wb, 1024u, kSw128);
+                const uint32_t idesc = layer2 ? idesc2 : idesc1;
+                const uint32_t first = layer2 ? (uint32_t)k2 : (uint32_t)kb;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(tmem, smem_desc(ab + ks * 32, 1024u, kSw128), smem_desc(wb + ks * 32, 1024u, kSw128),
-                                  idesc1, (kb | ks) != 0);
-                } else {
-                    const int k2 = kb - nslab1;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(tmem, kop_desc(smem_u32(a1), kFpTile, s.c1, k2 * 4 + ks, 0),
-                                  smem_desc(wb + ks * 32, 1024u, kSw128), idesc2, (k2 | ks) != 0);
-                }
-                umma_commit(smem_u32(mbar + st));
+                for (int ks = 0; ks < 4; ++ks)
+                    if (elected) umma_bf16(tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (first | ks) != 0);
+                if (elected) umma_commit(smem_u32(mbar + st));
+                __syncwarp();
             }
             if (st) ++uses1; else ++uses0;
         }

@@ -167,8 +167,8 @@ __device__ __forceinline__ void take_later_if_greater(Cand &a, const Cand &b)
 // P = point slots per thread (even).  REGS: xyz of the slots are kept in registers (P <= 16); otherwise
 // they are read back from this CTA's shared-memory copy each round.  CLUSTER: compiled-in switch
 // between the single-CTA exchange (shared memory + bar.sync) and the DSMEM exchange.
-template <int P, bool REGS, bool CLUSTER, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+template <int P, bool REGS, bool CLUSTER, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int *__restrict__ idxs,
            float *__restrict__ new_xyz, long long *__restrict__ prof)
 {
@@ -404,7 +404,12 @@ template <int P, bool REGS, int MAXT>
 static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
                   long long *prof, cudaStream_t stream)
 {
-    auto kern = pl.cluster > 1 ? fps_kernel<P, REGS, true, MAXT> : fps_kernel<P, REGS, false, MAXT>;
+    // large clusters of 256-thread CTAs: a second variant capped at 128 registers lets two CTAs share an SM
+    // (twice the scenes in flight when several batches run concurrently)
+    static const bool two_per_sm = [] { const char *e = getenv("PN2_FPS_MINB"); return e && atoi(e) == 2; }();
+    auto kern = pl.cluster > 1 ? ((MAXT <= 256 && P >= 16 && two_per_sm) ? fps_kernel<P, REGS, true, MAXT, (MAXT <= 256 && P >= 16) ? 2 : 1>
+                                                                         : fps_kernel<P, REGS, true, MAXT, 1>)
+                               : fps_kernel<P, REGS, false, MAXT, 1>;
     const size_t smem = (size_t)3 * P * pl.threads * sizeof(float);
     PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (pl.cluster > 8)

@@ -161,6 +161,7 @@ struct SaTcParams {
     SaTcShape s;
     int n, npoint, tiles_per_scene, ntiles;
     int nstage;             // gather ring depth of the warp-specialised kernel (2..4)
+    long long *prof;        // diagnostics: per-phase SM cycles of CTA 0 (16 x int64) or NULL
     float inv_radius;
     const float *xyz, *new_xyz;
     const __nv_bfloat16 *table;
@@ -341,11 +342,12 @@ sa_tc_kernel(const SaTcParams p)
         __syncthreads();
 
         // ---- layer 1 ----
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            for (int ks = 0; ks < s.k0 / 16; ++ks)
-                umma_bf16(tmem, kop_desc(a_base, kTile, s.k0, ks, 0), kop_desc(w1_base, s.c1, s.k0, ks, 0), idesc1, ks > 0);
-            umma_commit(smem_u32(mbar));
+            const uint32_t elected = elect_one();
+            issue_gemm(tmem, a_base, kTile, 0, w1_base, s.c1, 0, s.k0, idesc1, elected);
+            if (elected) umma_commit(smem_u32(mbar));
+            __syncwarp();
         }
         tc_mbar_wait(smem_u32(mbar), phase);
         phase ^= 1;
@@ -360,11 +362,12 @@ sa_tc_kernel(const SaTcParams p)
         __syncthreads();
 
         // ---- layer 2 ----
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            for (int ks = 0; ks < s.c1 / 16; ++ks)
-                umma_bf16(tmem, kop_desc(a_base, kTile, s.c1, ks, 0), kop_desc(w2_base, s.c2, s.c1, ks, 0), idesc2, ks > 0);
-            umma_commit(smem_u32(mbar));
+            const uint32_t elected = elect_one();
+            issue_gemm(tmem, a_base, kTile, 0, w2_base, s.c2, 0, s.c1, idesc2, elected);
+            if (elected) umma_commit(smem_u32(mbar));
+            __syncwarp();
         }
         tc_mbar_wait(smem_u32(mbar), phase);
         phase ^= 1;
@@ -376,13 +379,13 @@ sa_tc_kernel(const SaTcParams p)
         __syncthreads();
 
         // ---- layer 3 (channels on the TMEM lanes) ----
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
+            const uint32_t elected = elect_one();
             for (int mt = 0; mt < s.c3 / 128; ++mt)
-                for (int ks = 0; ks < s.c2 / 16; ++ks)
-                    umma_bf16(tmem + mt * kTile, kop_desc(w3_base, s.c3, s.c2, ks, mt * 128),
-                              kop_desc(a_base, kTile, s.c2, ks, 0), idesc3, ks > 0);
-            umma_commit(smem_u32(mbar));
+                issue_gemm(tmem + mt * kTile, w3_base, s.c3, mt * 128, a_base, kTile, 0, s.c2, idesc3, elected);
+            if (elected) umma_commit(smem_u32(mbar));
+            __syncwarp();
         }
         tc_mbar_wait(smem_u32(mbar), phase);
         phase ^= 1;
@@ -431,7 +434,6 @@ sa_tc_pipe_kernel(const SaTcParams p)
     float *bias3 = bias2 + s.c2;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(bias3 + s.c3);            // full[4], empty[4], mma
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 9);
-    __shared__ int s_idx[kMaxStages][kTile];
     const int nstage = p.nstage;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -461,43 +463,68 @@ sa_tc_pipe_kernel(const SaTcParams p)
 
     if (warp >= kPipeConsumers / 32) {
         // ===== gather warps =====
-        const int ptid = tid - kPipeConsumers, pwarp = warp - kPipeConsumers / 32;
+        // Two lanes share a row: lane pair (2j, 2j+1) of producer thread ptid copies the even / odd 16-byte
+        // chunks of rows ptid/2 and ptid/2 + 64, so one cp.async instruction moves 32 contiguous bytes of 16
+        // rows (whole L2 sectors) and every thread's work is a flat, independent list of copies.
+        const int ptid = tid - kPipeConsumers;
+        const int sub = ptid & 1, r0 = ptid >> 1, r1 = r0 + 64;
+        const uint32_t sw0 = (uint32_t)(r0 & 7), sw1 = (uint32_t)(r1 & 7);
+        const int nfull8 = (s.k0 / 64) * 8;                      // chunks that live in 128B-swizzled tiles
         int it = 0;
-        // the neighbour index of this thread's row is fetched one tile ahead
-        int nb_next = 0;
+        long long pc[4] = {0, 0, 0, 0}, tprev = 0;
+        const bool profiling = p.prof != nullptr && blockIdx.x == 0 && ptid == 0;
+        if (profiling) tprev = clock64();
+#define PN2_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
+        // neighbour indices of this thread's two rows, fetched one tile ahead
+        int nb0_next = 0, nb1_next = 0;
         if ((int)blockIdx.x < p.ntiles) {
             const int bi0 = blockIdx.x / p.tiles_per_scene;
-            nb_next = __ldg(p.idx + (size_t)bi0 * p.npoint * NS + (blockIdx.x - bi0 * p.tiles_per_scene) * kTile + ptid);
+            const int *ip = p.idx + (size_t)bi0 * p.npoint * NS + (blockIdx.x - bi0 * p.tiles_per_scene) * kTile;
+            nb0_next = __ldg(ip + r0); nb1_next = __ldg(ip + r1);
         }
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const int st = it % nstage, u = it / nstage;
-            const int nb = nb_next;
+            const int nb0 = nb0_next, nb1 = nb1_next;
             {
                 const int nt = tile + gridDim.x;
                 if (nt < p.ntiles) {
                     const int bn = nt / p.tiles_per_scene;
-                    nb_next = __ldg(p.idx + (size_t)bn * p.npoint * NS + (nt - bn * p.tiles_per_scene) * kTile + ptid);
+                    const int *ip = p.idx + (size_t)bn * p.npoint * NS + (nt - bn * p.tiles_per_scene) * kTile;
+                    nb0_next = __ldg(ip + r0); nb1_next = __ldg(ip + r1);
                 }
             }
             if (u > 0) tc_mbar_wait(smem_u32(mbar + kMaxStages + st), (u - 1) & 1);   // the tile that used this stage is done
+            PN2_MARK(0)
             unsigned char *region = ring + st * s.region_bytes;
             const uint32_t a_base = smem_u32(region);
             const int bi = tile / p.tiles_per_scene;
             const int row0 = (tile - bi * p.tiles_per_scene) * kTile;
             const int centre0 = row0 / NS;
-            s_idx[st][ptid] = nb;
-            named_bar_sync(2, kPipeProducers);
-            // feature rows: no wait here -- the stage's "full" barrier is armed to fire when the copies land,
-            // so the gather warps run up to nstage tiles ahead of the tensor core
-            for (int r = pwarp; r < kTile; r += kPipeProducers / 32) {
-                const __nv_bfloat16 *src = p.table + ((size_t)bi * p.n + s_idx[st][r]) * s.row_elems;
-                for (int ch = lane; ch < nchunk; ch += 32)
-                    cp_async16(a_base + kop_chunk_off(kTile, s.k0, r, ch), src + ch * 8);
+            const __nv_bfloat16 *src0 = p.table + ((size_t)bi * p.n + nb0) * s.row_elems;
+            const __nv_bfloat16 *src1 = p.table + ((size_t)bi * p.n + nb1) * s.row_elems;
+            // no wait here: the stage's "full" barrier fires when the copies land, so the gather warps run
+            // up to nstage tiles ahead of the tensor core
+#pragma unroll 4
+            for (int ch = sub; ch < nchunk; ch += 2) {
+                uint32_t o0, o1;
+                if (ch < nfull8) {
+                    const uint32_t t = (uint32_t)(ch >> 3) * (kTile * 128u);
+                    o0 = t + r0 * 128u + ((((uint32_t)ch & 7u) ^ sw0) << 4);
+                    o1 = t + r1 * 128u + ((((uint32_t)ch & 7u) ^ sw1) << 4);
+                } else {
+                    o0 = kop_chunk_off(kTile, s.k0, r0, ch);
+                    o1 = kop_chunk_off(kTile, s.k0, r1, ch);
+                }
+                cp_async16(a_base + o0, src0 + ch * 8);
+                cp_async16(a_base + o1, src1 + ch * 8);
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar + st)) : "memory");
+            PN2_MARK(1)
             {
+                // xyz chunk (+ zero padding) of one of the two rows per lane of the pair
+                const int row = sub ? r1 : r0, nb = sub ? nb1 : nb0;
                 const float *pp = p.xyz + ((size_t)bi * p.n + nb) * 3;
-                const float *cc = p.new_xyz + ((size_t)bi * p.npoint + centre0 + ptid / NS) * 3;
+                const float *cc = p.new_xyz + ((size_t)bi * p.npoint + centre0 + row / NS) * 3;
                 float h[3], l[3];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
@@ -505,23 +532,26 @@ sa_tc_pipe_kernel(const SaTcParams p)
                     h[a] = __bfloat162float(__float2bfloat16_rn(d));
                     l[a] = d - h[a];
                 }
-                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, ptid, xchunk)) =
+                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, row, xchunk)) =
                     make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], l[0]), pack_bf16(l[1], l[2]), pack_bf16(1.f, 1.f));
                 for (int ch = xchunk + 1; ch < k0chunks; ++ch)
-                    *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, ptid, ch)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, row, ch)) = make_uint4(0u, 0u, 0u, 0u);
             }
             fence_proxy_async();
             tc_mbar_arrive(smem_u32(mbar + st));                                   // release of the xyz chunk
+            PN2_MARK(2)
         }
         cp_async_wait_all();
+        if (profiling) { for (int i = 0; i < 3; ++i) p.prof[8 + i] = pc[i]; p.prof[11] = it; }
+#undef PN2_MARK
     } else {
         // ===== MMA + epilogue warps: warp w works on TMEM lanes 32*(w%4).. and on column half w/4 =====
         const int quarter = warp & 3, half = warp >> 2;
         const int row = quarter * 32 + lane;                                    // TMEM lane = sample row / channel
         const uint32_t my_tmem = tmem + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t w1_base = smem_u32(w1s), w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
         const uint32_t idesc1 = umma_idesc(kTile, s.c1), idesc2 = umma_idesc(kTile, s.c2), idesc3 = umma_idesc(128, kTile);
         const uint32_t mma_bar = smem_u32(mbar + 2 * kMaxStages);
+        const uint32_t w1_base = smem_u32(w1s), w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
         // column ranges of this warp's half (multiples of 32)
         const int h1 = ((s.c1 / 2 + 31) / 32) * 32, h2 = ((s.c2 / 2 + 31) / 32) * 32;
         const int c1_lo = half ? h1 : 0, c1_hi = half ? s.c1 : min(h1, s.c1);
@@ -530,6 +560,10 @@ sa_tc_pipe_kernel(const SaTcParams p)
         const int s_lo = NS <= 64 ? half * 64 : 0, s_hi = NS <= 64 ? half * 64 + 64 : (half ? 0 : kTile);
         uint32_t phase = 0;
         int it = 0;
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+        const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        if (profiling) tprev = clock64();
+#define PN2_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const int st = it % nstage, u = it / nstage;
             unsigned char *region = ring + st * s.region_bytes;
@@ -537,48 +571,61 @@ sa_tc_pipe_kernel(const SaTcParams p)
             const int bi = tile / p.tiles_per_scene;
             const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
             tc_mbar_wait(smem_u32(mbar + st), u & 1);                          // gathered
+            PN2_MARK(0)
             fence_proxy_async();          // the gather's cp.async / st.shared writes -> visible to the tensor core
             tc_fence_after();
-            if (tid == 0) {
-                for (int ks = 0; ks < s.k0 / 16; ++ks)
-                    umma_bf16(tmem, kop_desc(a_base, kTile, s.k0, ks, 0), kop_desc(w1_base, s.c1, s.k0, ks, 0), idesc1, ks > 0);
-                umma_commit(mma_bar);
+            if (warp == 0) {
+                const uint32_t elected = elect_one();
+                issue_gemm(tmem, a_base, kTile, 0, w1_base, s.c1, 0, s.k0, idesc1, elected);
+                if (elected) umma_commit(mma_bar);
+                __syncwarp();
             }
             tc_mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
+            PN2_MARK(1)
             epilogue_act(my_tmem, region, s.c1, row, c1_lo, c1_hi, nullptr);
             tc_fence_before();
             fence_proxy_async();
             named_bar_sync(1, kPipeConsumers);
-            if (tid == 0) {
+            PN2_MARK(2)
+            if (warp == 0) {
                 tc_fence_after();
-                for (int ks = 0; ks < s.c1 / 16; ++ks)
-                    umma_bf16(tmem, kop_desc(a_base, kTile, s.c1, ks, 0), kop_desc(w2_base, s.c2, s.c1, ks, 0), idesc2, ks > 0);
-                umma_commit(mma_bar);
+                const uint32_t elected = elect_one();
+                issue_gemm(tmem, a_base, kTile, 0, w2_base, s.c2, 0, s.c1, idesc2, elected);
+                if (elected) umma_commit(mma_bar);
+                __syncwarp();
             }
             tc_mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
+            PN2_MARK(3)
             epilogue_act(my_tmem, region, s.c2, row, c2_lo, c2_hi, bias2);
             tc_fence_before();
             fence_proxy_async();
             named_bar_sync(1, kPipeConsumers);
-            if (tid == 0) {
+            PN2_MARK(4)
+            if (warp == 0) {
                 tc_fence_after();
+                const uint32_t elected = elect_one();
                 for (int mt = 0; mt < s.c3 / 128; ++mt)
-                    for (int ks = 0; ks < s.c2 / 16; ++ks)
-                        umma_bf16(tmem + mt * kTile, kop_desc(w3_base, s.c3, s.c2, ks, mt * 128),
-                                  kop_desc(a_base, kTile, s.c2, ks, 0), idesc3, ks > 0);
-                umma_commit(mma_bar);
-                umma_commit(smem_u32(mbar + kMaxStages + st));                  // stage free for the gather warps
+                    issue_gemm(tmem + mt * kTile, w3_base, s.c3, mt * 128, a_base, kTile, 0, s.c2, idesc3, elected);
+                if (elected) {
+                    umma_commit(mma_bar);
+                    umma_commit(smem_u32(mbar + kMaxStages + st));              // stage free for the gather warps
+                }
+                __syncwarp();
             }
             tc_mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
+            PN2_MARK(5)
             if (s_lo < s_hi)
                 for (int mt = 0; mt < s.c3 / 128; ++mt)
                     epilogue_pool<NS>(p, my_tmem + mt * kTile, bi, centre0, mt * 128 + row, bias3[mt * 128 + row], s_lo, s_hi);
             tc_fence_before();
             named_bar_sync(1, kPipeConsumers);   // every epilogue warp is done with TMEM before the next tile's MMA
+            PN2_MARK(6)
         }
+        if (profiling) { for (int i = 0; i < 7; ++i) p.prof[i] = pc[i]; p.prof[7] = it; }
+#undef PN2_MARK
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
@@ -684,6 +731,14 @@ static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
 
 using namespace pn2;
 
+// diagnostics: when set, the next pn2_sa_tc_forward launches record per-phase cycles of CTA 0 there
+static long long *g_sa_tc_prof = nullptr;
+extern "C" int pn2_debug_sa_tc_profile(long long *prof)
+{
+    g_sa_tc_prof = prof;
+    return PN2_OK;
+}
+
 extern "C" int pn2_sa_tc_row_elems(int c) { return c < 0 ? 0 : rup(c, 8); }
 
 extern "C" int pn2_sa_tc_supported(int c, int c1, int c2, int c3, int npoint, int nsample)
@@ -765,6 +820,7 @@ extern "C" int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, i
     p.out = out;
     p.out_table = static_cast<__nv_bfloat16 *>(out_table);
     p.nstage = 0;
+    p.prof = g_sa_tc_prof;
     switch (nsample) {
     case 16: return launch_sa_tc<16>(p, as_stream(stream));
     case 32: return launch_sa_tc<32>(p, as_stream(stream));

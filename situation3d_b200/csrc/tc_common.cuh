@@ -112,6 +112,40 @@ __device__ __forceinline__ uint64_t kop_desc(uint32_t base, int rows, int K, int
                      kSw32);
 }
 
+// one elected lane of a converged warp (the other lanes get 0)
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t e;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(e));
+    return e;
+}
+
+// D[tmem_d] = A (a_rows x K at a_base, first row a_r0) * B (b_rows x K at b_base, first row b_r0)^T, issued by
+// the elected lane of a converged warp.  Called by ALL lanes: the descriptors are computed warp-uniformly
+// (uniform registers) and only the tcgen05.mma itself is predicated -- measured on B200 this issues an MMA
+// every ~45 cycles instead of ~70 when a single thread builds the descriptors in vector registers.
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_base, int a_rows, int a_r0, uint32_t b_base,
+                                           int b_rows, int b_r0, int K, uint32_t idesc, uint32_t elected)
+{
+    const int nfull = K >> 6, ntail = (K & 63) >> 4;
+    const uint64_t da = smem_desc(a_base + (uint32_t)a_r0 * 128u, 1024u, kSw128);
+    const uint64_t db = smem_desc(b_base + (uint32_t)b_r0 * 128u, 1024u, kSw128);
+    const uint32_t a_step = (uint32_t)a_rows * 8u, b_step = (uint32_t)b_rows * 8u;   // 128-byte rows, 16-byte units
+    for (int kb = 0; kb < nfull; ++kb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (elected)
+                umma_bf16(tmem_d, da + (uint64_t)(kb * a_step + j * 2), db + (uint64_t)(kb * b_step + j * 2), idesc,
+                          (uint32_t)((kb | j) != 0));
+    }
+    const uint32_t a_tail = a_base + (uint32_t)nfull * a_rows * 128u + (uint32_t)a_r0 * 32u;
+    const uint32_t b_tail = b_base + (uint32_t)nfull * b_rows * 128u + (uint32_t)b_r0 * 32u;
+    for (int t = 0; t < ntail; ++t)
+        if (elected)
+            umma_bf16(tmem_d, smem_desc(a_tail + (uint32_t)t * a_rows * 32u, 256u, kSw32),
+                      smem_desc(b_tail + (uint32_t)t * b_rows * 32u, 256u, kSw32), idesc, (uint32_t)((nfull | t) != 0));
+}
+
 // instruction descriptor: D f32, A/B bf16, both K-major, N at [17,23) in units of 8, M at [24,29) in units of 16
 __host__ __device__ inline uint32_t umma_idesc(int M, int N)
 {
