@@ -406,7 +406,7 @@ static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int 
 {
     // large clusters of 256-thread CTAs: a second variant capped at 128 registers lets two CTAs share an SM
     // (twice the scenes in flight when several batches run concurrently)
-    static const bool two_per_sm = [] { const char *e = getenv("PN2_FPS_MINB"); return e && atoi(e) == 2; }();
+    static const bool two_per_sm = [] { const char *e = getenv("PN2_FPS_MINB"); return !e || atoi(e) == 2; }();
     auto kern = pl.cluster > 1 ? ((MAXT <= 256 && P >= 16 && two_per_sm) ? fps_kernel<P, REGS, true, MAXT, (MAXT <= 256 && P >= 16) ? 2 : 1>
                                                                          : fps_kernel<P, REGS, true, MAXT, 1>)
                                : fps_kernel<P, REGS, false, MAXT, 1>;
