@@ -317,3 +317,21 @@ def test_backbone_stress_config5_shape():
         out = net.cuda()({"point_clouds": pc.cuda()})
     _check_backbone(out, want, "bf16")
     assert out["fp2_features"].shape == (1, 256, 2048)
+
+
+def test_training_step_config4_single_gpu():
+    """BASELINE.json config 4 on one GPU (the all-reduce is a no-op at world size 1; the N > 1 exchange is
+    covered by tests/test_dist_cpu.py over gloo): loss is finite, decreases, every parameter moves."""
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.synthetic import make_batch
+    from situation3d_b200.train_step import BackboneTrainer
+    torch.manual_seed(0)
+    net = Pointnet2Backbone(input_feature_dim=9, npoints=(256, 128, 64, 32)).cuda()
+    before = [p.detach().clone() for p in net.parameters()]
+    tr = BackboneTrainer(net, lr=1e-2)
+    pc = torch.from_numpy(make_batch(2, 3000, 9, first_seed=50)).cuda()
+    losses = [float(tr.step(pc)) for _ in range(4)]
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
+    assert all(not torch.equal(a, b) for a, b in zip(before, net.parameters()))
+    for p_, v in zip(net.parameters(), tr.bucket.views):
+        assert p_.grad.data_ptr() == v.data_ptr()
