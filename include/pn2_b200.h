@@ -205,8 +205,9 @@ int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, int c1, int 
                       const int *idx, const void *known_rows, const void *skip_rows,
                       const void *weight_image, float *out, void *out_rows, pn2_stream_t stream);
 
-/* Diagnostic: while prof (device, 16 x int64) is non-NULL, the warp-specialised pn2_sa_tc_forward kernel
- * records the SM cycles CTA 0 spends per phase ([0..6] MMA/epilogue warps, [7] tiles, [8..10] gather warps). */
+/* Diagnostic: while prof (device, 32 x int64) is non-NULL, the pn2_sa_tc_forward kernels record the SM cycles
+ * CTA 0 spends per phase.  Software-pipelined kernel: [0..5] epilogue warp 0 (wait D1, E1, wait D2, E2, wait D3,
+ * E3), [7] tiles, [8..10] layer-1 issuer, [11..14] layer-2/3 issuer, [16..18] gather warps. */
 int pn2_debug_sa_tc_profile(long long *prof);
 
 /* Diagnostic: D (128 x n f32) = A (128 x k bf16) * B^T (n x k bf16) through the same shared-memory

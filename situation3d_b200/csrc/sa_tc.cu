@@ -161,6 +161,9 @@ struct SaTcParams {
     SaTcShape s;
     int n, npoint, tiles_per_scene, ntiles;
     int nstage;             // gather ring depth of the warp-specialised kernel (2..4)
+    int nregion, nslot;     // pipelined kernel: shared-memory tile regions (<= 8) and TMEM accumulator slots (2 or 4)
+    uint32_t blk;
+    int debug;              // diagnostics (PN2_SA_TC_DEBUG): bit 0 skip the feature gather, bit 1 skip the xyz chunk
     long long *prof;        // diagnostics: per-phase SM cycles of CTA 0 (16 x int64) or NULL
     float inv_radius;
     const float *xyz, *new_xyz;
@@ -631,6 +634,433 @@ sa_tc_pipe_kernel(const SaTcParams p)
     if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
+
+// ---- software-pipelined variant: several tiles in flight through the three layers --------------------
+// The kernels above run a tile's chain  gather -> MMA1 -> epi1 -> MMA2 -> epi2 -> MMA3 -> epi3  strictly in
+// sequence; every arrow is a synchronisation (tcgen05.commit -> mbarrier -> wake-up, or epilogue -> proxy
+// fence -> barrier) of several hundred cycles during which the tensor pipe idles (ncu: 10 % busy at SA1).
+// Here T tiles (T = 512 / TMEM columns per tile: 4 at SA1, 2 for the 256-wide layers) are in flight at
+// once, each in its own shared-memory region and TMEM slot, and the roles are separate warps that only
+// meet at mbarriers:
+//   warps 0-3 / 4-7  two epilogue groups; group g owns the slots s = g (mod 2).  Per wave of T tiles a
+//                    group runs E1 of its slots, then E2, then E3.
+//   warp 8           issues layer 1 of tile after tile (needs: region gathered, slot's previous E3 done)
+//   warp 9           issues layers 2 and 3 in wave order
+//   warps 12-15      gather, up to R - T tiles ahead of the tensor core (R regions, as many as fit)
+// Every dependency points backwards in the wave order (R >= T), so the schedule cannot deadlock.
+// Layer widths are compile-time, so the epilogues are straight-line code.  Layer-1 activations never
+// touch shared memory: E1 writes them as packed bf16 back into TMEM and layer 2 reads its A operand from
+// there (tcgen05.mma with A in TMEM), which removes a swizzled store pass, a generic->async proxy fence
+// and a quarter of the shared-memory operand traffic per tile.
+constexpr int kV3EpiThreads = 256;
+constexpr int kV3WarpA = 8, kV3WarpB = 9, kV3ProdWarp0 = 12;   // warps 10, 11 idle (registers are allocated per 4 warps)
+constexpr int kV3Producers = 128;
+constexpr int kV3Threads = 512;
+constexpr int kV3MaxRegions = 8, kV3MaxSlots = 4;
+constexpr int kV3Bars = 2 * kV3MaxRegions + kV3MaxSlots * 6;    // full, empty | dfull[s][3], aready[s][2], tfree[s]
+
+__device__ __forceinline__ void umma_bf16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// E1: D1 (fp32, this thread's row) -> ReLU -> bf16 pairs -> TMEM columns of the layer-2 A operand
+template <int C1>
+__device__ __forceinline__ void v3_epi1(uint32_t d_taddr, uint32_t a_taddr)
+{
+#pragma unroll
+    for (int c0 = 0; c0 < C1; c0 += 64) {
+        uint32_t va[32], vb[32];
+        tmem_ld32_issue(d_taddr + c0, va);
+        tmem_ld32_issue(d_taddr + c0 + 32, vb);
+        tmem_ld_wait();
+        uint32_t pa[16], pb[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            pa[j] = pack_bf16_relu(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+            pb[j] = pack_bf16_relu(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+        }
+        tmem_st16(a_taddr + c0 / 2, pa);
+        tmem_st16(a_taddr + c0 / 2 + 16, pb);
+    }
+    tmem_st_wait();
+}
+
+// E2: D2 + bias -> ReLU -> bf16 -> K-major 128B-swizzled rows of the region (the layer-3 B operand)
+template <int C2>
+__device__ __forceinline__ void v3_epi2(uint32_t d_taddr, unsigned char *region, int row, const float *bias2)
+{
+    unsigned char *row_base = region + row * 128;
+    const uint32_t r7 = (uint32_t)(row & 7);
+#pragma unroll
+    for (int c0 = 0; c0 < C2; c0 += 64) {
+        uint32_t v[2][32];
+        tmem_ld32_issue(d_taddr + c0, v[0]);
+        tmem_ld32_issue(d_taddr + c0 + 32, v[1]);
+        tmem_ld_wait();
+        unsigned char *tile_base = row_base + (c0 / 64) * (kTile * 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b0 = *reinterpret_cast<const float4 *>(bias2 + c0 + h * 32 + q * 8);
+                const float4 b1 = *reinterpret_cast<const float4 *>(bias2 + c0 + h * 32 + q * 8 + 4);
+                const int j = q * 8;
+                const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[h][j]) + b0.x, __uint_as_float(v[h][j + 1]) + b0.y);
+                const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[h][j + 2]) + b0.z, __uint_as_float(v[h][j + 3]) + b0.w);
+                const uint32_t w2 = pack_bf16_relu(__uint_as_float(v[h][j + 4]) + b1.x, __uint_as_float(v[h][j + 5]) + b1.y);
+                const uint32_t w3 = pack_bf16_relu(__uint_as_float(v[h][j + 6]) + b1.z, __uint_as_float(v[h][j + 7]) + b1.w);
+                *reinterpret_cast<uint4 *>(tile_base + (((uint32_t)(h * 4 + q) ^ r7) << 4)) = make_uint4(w0, w1, w2, w3);
+            }
+    }
+}
+
+// E3: channel `ch` (this thread's TMEM lane) of the 128 sample columns: max over each centre's NS columns,
+// + bias, ReLU; fp32 (B,C3,npoint) for the API and bf16 channel-last rows for the next layer
+template <int NS, int C3>
+__device__ __forceinline__ void v3_epi3(const SaTcParams &p, uint32_t d_taddr, int bi, int centre0, int lane_row,
+                                        const float *bias3)
+{
+#pragma unroll
+    for (int mt = 0; mt < C3 / 128; ++mt) {
+        const int ch = mt * 128 + lane_row;
+        const float bias = bias3[ch];
+        float *out = p.out + ((size_t)bi * C3 + ch) * p.npoint + centre0;
+        __nv_bfloat16 *out_t = p.out_table ? p.out_table + ((size_t)bi * p.npoint + centre0) * C3 + ch : nullptr;
+        float run = -3.0e38f;
+#pragma unroll
+        for (int q0 = 0; q0 < kTile; q0 += 64) {
+            uint32_t v[2][32];
+            tmem_ld32_issue(d_taddr + mt * kTile + q0, v[0]);
+            tmem_ld32_issue(d_taddr + mt * kTile + q0 + 32, v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = q0 + h * 32;
+                if (NS >= 32) {
+                    float m0 = fmaxf(__uint_as_float(v[h][0]), __uint_as_float(v[h][1]));
+                    float m1 = fmaxf(__uint_as_float(v[h][2]), __uint_as_float(v[h][3]));
+#pragma unroll
+                    for (int j = 4; j < 32; j += 2) {
+                        m0 = fmaxf(m0, __uint_as_float(v[h][j]));
+                        m1 = fmaxf(m1, __uint_as_float(v[h][j + 1]));
+                    }
+                    run = fmaxf(run, fmaxf(m0, m1));
+                    if ((col + 32) % NS == 0) {
+                        const int cl = col / NS;
+                        const float o = fmaxf(run + bias, 0.f);
+                        out[cl] = o;
+                        if (out_t) out_t[(size_t)cl * C3] = __float2bfloat16_rn(o);
+                        run = -3.0e38f;
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 32 / NS; ++g) {
+                        float mx = __uint_as_float(v[h][g * NS]);
+#pragma unroll
+                        for (int j = 1; j < NS; ++j) mx = fmaxf(mx, __uint_as_float(v[h][g * NS + j]));
+                        const int cl = col / NS + g;
+                        const float o = fmaxf(mx + bias, 0.f);
+                        out[cl] = o;
+                        if (out_t) out_t[(size_t)cl * C3] = __float2bfloat16_rn(o);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NS, int C1, int C2, int C3, bool PROF>
+__global__ void __launch_bounds__(kV3Threads, 1)
+sa_tc_v3_kernel(const SaTcParams p)
+{
+    static_assert(C1 % 64 == 0 && C2 % 64 == 0 && C3 % 128 == 0, "whole swizzle tiles");
+    constexpr int kAOff = C1 > C2 ? C1 : C2;                               // TMEM column of the layer-2 A operand
+    constexpr int kBlkNeed = (kAOff + C1 / 2) > C3 ? (kAOff + C1 / 2) : C3;
+    constexpr uint32_t kBlk = kBlkNeed <= 128 ? 128 : 256;                 // TMEM columns per slot
+    constexpr int T = 512 / kBlk;
+    static_assert(kBlkNeed <= 256, "TMEM slot");
+    extern __shared__ unsigned char smem_raw[];
+    const SaTcShape &s = p.s;
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const uint32_t resident = s.w1_bytes + s.w2_bytes + s.w3_bytes;
+    unsigned char *w1s = base, *w2s = base + s.w1_bytes, *w3s = base + s.w1_bytes + s.w2_bytes;
+    unsigned char *ring = base + resident;
+    const int R = p.nregion;
+    float *bias2 = reinterpret_cast<float *>(ring + (size_t)R * s.region_bytes);
+    float *bias3 = bias2 + C2;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(bias3 + C3);
+    const uint32_t bar_full = smem_u32(mbar), bar_empty = bar_full + 8u * kV3MaxRegions,
+                   bar_dfull = bar_empty + 8u * kV3MaxRegions, bar_aready = bar_dfull + 8u * 3 * kV3MaxSlots,
+                   bar_tfree = bar_aready + 8u * 2 * kV3MaxSlots;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + kV3Bars);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.image);
+        for (uint32_t i = tid; i < resident / 16; i += kV3Threads) cp_async16(smem_u32(base) + i * 16, src + i);
+        const float *bsrc = reinterpret_cast<const float *>(p.image + resident);
+        for (int i = tid; i < C2 + C3; i += kV3Threads) bias2[i] = __ldg(bsrc + i);
+        if (tid == 0) {
+            for (int i = 0; i < kV3MaxRegions; ++i) {
+                tc_mbar_init(bar_full + 8u * i, 2 * kV3Producers);   // cp.async completion + explicit arrival per gather thread
+                tc_mbar_init(bar_empty + 8u * i, 1);                 // tcgen05.commit after the tile's last MMA
+            }
+            for (int i = 0; i < 3 * kV3MaxSlots; ++i) tc_mbar_init(bar_dfull + 8u * i, 1);    // tcgen05.commit
+            for (int i = 0; i < 2 * kV3MaxSlots; ++i) tc_mbar_init(bar_aready + 8u * i, 4);   // one arrival per warp of the group
+            for (int i = 0; i < kV3MaxSlots; ++i) tc_mbar_init(bar_tfree + 8u * i, 4);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 0) tmem_alloc<512>(smem_u32(tmem_slot));
+        cp_async_wait_all();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = *tmem_slot;
+    const int nt = (int)blockIdx.x < p.ntiles ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const bool prof_cta = PROF && p.prof != nullptr && blockIdx.x == 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
+#define PN2_MARK(i) if (PROF) { if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; } }
+
+    if (warp >= kV3ProdWarp0) {
+        // ===== gather warps: warp pw copies rows pw*32 .. pw*32+31 of the tile =====
+        // A cp.async instruction covers two whole rows (lanes 0-15 / 16-31 take 16 consecutive 16-byte chunks
+        // each), so it touches the 5-6 cache lines those rows occupy instead of 16-32 lines of as many rows;
+        // the chunks left over (row_elems/8 mod 16) are copied 32/rem rows at a time.
+        const int pw = warp - kV3ProdWarp0;
+        const int myrow = pw * 32 + lane;
+        const int nchunk = s.row_elems / 8, xchunk = nchunk, k0chunks = s.k0 / 8;
+        const int nfull16 = nchunk & ~15, rem = nchunk & 15;
+        const bool profiling = prof_cta && tid == kV3ProdWarp0 * 32;
+        if (PROF) { if (profiling) tprev = clock64(); }
+        int nb_next = 0;
+        if (nt > 0) {
+            const int t0 = blockIdx.x, bi0 = t0 / p.tiles_per_scene;
+            nb_next = __ldg(p.idx + (size_t)bi0 * p.npoint * NS + (t0 - bi0 * p.tiles_per_scene) * kTile + myrow);
+        }
+        for (int it = 0; it < nt; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int rg = it % R, u = it / R;
+            const int nb = nb_next;
+            if (it + 1 < nt) {
+                const int t1 = tile + gridDim.x, bn = t1 / p.tiles_per_scene;
+                nb_next = __ldg(p.idx + (size_t)bn * p.npoint * NS + (t1 - bn * p.tiles_per_scene) * kTile + myrow);
+            }
+            const int bi = tile / p.tiles_per_scene;
+            const int row0 = (tile - bi * p.tiles_per_scene) * kTile;
+            // recentred, normalised xyz of this lane's row (loads issued before the wait)
+            const float *pp = p.xyz + ((size_t)bi * p.n + nb) * 3;
+            const float *cc = p.new_xyz + ((size_t)bi * p.npoint + (row0 + myrow) / NS) * 3;
+            float h[3], l[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float d = __fmul_rn(__fsub_rn(__ldg(pp + a), __ldg(cc + a)), p.inv_radius);
+                h[a] = __bfloat162float(__float2bfloat16_rn(d));
+                l[a] = d - h[a];
+            }
+            if (u > 0) tc_mbar_wait(bar_empty + 8u * rg, (u - 1) & 1);
+            PN2_MARK(0)
+            unsigned char *region = ring + (size_t)rg * s.region_bytes;
+            const uint32_t a_base = smem_u32(region);
+            const __nv_bfloat16 *tab = p.table + (size_t)bi * p.n * s.row_elems;
+            if (!(p.debug & 1)) {
+                for (int cb = 0; cb < nfull16; cb += 16) {
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = 2 * i + (lane >> 4);
+                        const int nbr = __shfl_sync(0xffffffffu, nb, rr);
+                        const int ch = cb + (lane & 15);
+                        cp_async16(a_base + kop_chunk_off(kTile, s.k0, pw * 32 + rr, ch),
+                                   tab + (size_t)nbr * s.row_elems + ch * 8);
+                    }
+                }
+                if (rem) {
+                    for (int j = lane; j < 32 * rem; j += 32) {
+                        const int rr = j / rem, ch = nfull16 + (j - rr * rem);
+                        const int nbr = __shfl_sync(0xffffffffu, nb, rr);
+                        cp_async16(a_base + kop_chunk_off(kTile, s.k0, pw * 32 + rr, ch),
+                                   tab + (size_t)nbr * s.row_elems + ch * 8);
+                    }
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8u * rg) : "memory");
+            PN2_MARK(1)
+            *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, myrow, xchunk)) =
+                make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], l[0]), pack_bf16(l[1], l[2]), pack_bf16(1.f, 1.f));
+            for (int ch = xchunk + 1; ch < k0chunks; ++ch)
+                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, myrow, ch)) = make_uint4(0u, 0u, 0u, 0u);
+            fence_proxy_async();
+            tc_mbar_arrive(bar_full + 8u * rg);
+            PN2_MARK(2)
+        }
+        cp_async_wait_all();
+        if (PROF) { if (profiling) for (int i = 0; i < 3; ++i) p.prof[16 + i] = pc[i]; }
+    } else if (warp == kV3WarpA) {
+        // ===== layer-1 issuer =====
+        const uint32_t idesc1 = umma_idesc(kTile, C1);
+        const uint32_t w1_base = smem_u32(w1s);
+        const uint32_t elected = elect_one();
+        const bool profiling = prof_cta && lane == 0;
+        if (PROF) { if (profiling) tprev = clock64(); }
+        for (int it = 0; it < nt; ++it) {
+            const int sl = it % T, w = it / T, rg = it % R;
+            tc_mbar_wait(bar_full + 8u * rg, (it / R) & 1);                    // gathered
+            PN2_MARK(0)
+            if (w > 0) tc_mbar_wait(bar_tfree + 8u * sl, (w - 1) & 1);         // the slot's previous tile has left TMEM
+            PN2_MARK(1)
+            fence_proxy_async();
+            tc_fence_after();
+            issue_gemm(tmem + sl * kBlk, smem_u32(ring + (size_t)rg * s.region_bytes), kTile, 0, w1_base, C1, 0, s.k0,
+                       idesc1, elected);
+            if (elected) umma_commit(bar_dfull + 8u * (sl * 3 + 0));
+            __syncwarp();
+            PN2_MARK(2)
+        }
+        if (PROF) { if (profiling) for (int i = 0; i < 3; ++i) p.prof[8 + i] = pc[i]; }
+    } else if (warp == kV3WarpB) {
+        // ===== layer-2 / layer-3 issuer =====
+        const uint32_t idesc2 = umma_idesc(kTile, C2), idesc3 = umma_idesc(128, kTile);
+        const uint32_t w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
+        const uint64_t dw2 = smem_desc(w2_base, 1024u, kSw128);
+        const uint32_t elected = elect_one();
+        const bool profiling = prof_cta && lane == 0;
+        if (PROF) { if (profiling) tprev = clock64(); }
+        for (int w = 0, it0 = 0; it0 < nt; ++w, it0 += T) {
+            const int cnt = min(T, nt - it0);
+            for (int sl = 0; sl < cnt; ++sl) {
+                tc_mbar_wait(bar_aready + 8u * (sl * 2 + 0), w & 1);           // A1 in TMEM, D1 drained
+                PN2_MARK(0)
+                tc_fence_after();
+                const uint32_t d = tmem + sl * kBlk;
+#pragma unroll
+                for (int ks = 0; ks < C1 / 16; ++ks)
+                    if (elected)
+                        umma_bf16_ta(d, d + kAOff + ks * 8, dw2 + (uint64_t)((ks >> 2) * (C2 * 8) + (ks & 3) * 2), idesc2,
+                                     (uint32_t)(ks != 0));
+                if (elected) umma_commit(bar_dfull + 8u * (sl * 3 + 1));
+                __syncwarp();
+                PN2_MARK(1)
+            }
+            for (int sl = 0; sl < cnt; ++sl) {
+                const int rg = (it0 + sl) % R;
+                tc_mbar_wait(bar_aready + 8u * (sl * 2 + 1), w & 1);           // A2 in the region, D2 drained
+                PN2_MARK(2)
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(ring + (size_t)rg * s.region_bytes);
+#pragma unroll
+                for (int mt = 0; mt < C3 / 128; ++mt)
+                    issue_gemm(tmem + sl * kBlk + mt * kTile, w3_base, C3, mt * 128, a_base, kTile, 0, C2, idesc3, elected);
+                if (elected) {
+                    umma_commit(bar_dfull + 8u * (sl * 3 + 2));
+                    umma_commit(bar_empty + 8u * rg);                           // region free for the gather warps
+                }
+                __syncwarp();
+                PN2_MARK(3)
+            }
+        }
+        if (PROF) { if (profiling) for (int i = 0; i < 4; ++i) p.prof[11 + i] = pc[i]; }
+    } else if (warp < kV3EpiThreads / 32) {
+        // ===== epilogue groups: group g = warp / 4 owns slots g, g + 2; warp w works on TMEM lanes 32*(w%4).. =====
+        const int quarter = warp & 3, grp = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t my_tmem = tmem + ((uint32_t)(quarter * 32) << 16);
+        const bool profiling = prof_cta && tid == 0;
+        if (PROF) { if (profiling) tprev = clock64(); }
+        for (int w = 0, it0 = 0; it0 < nt; ++w, it0 += T) {
+            const int cnt = min(T, nt - it0);
+            const uint32_t ph = (uint32_t)(w & 1);
+            for (int sl = grp; sl < cnt; sl += 2) {
+                tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 0), ph);
+                tc_fence_after();
+                PN2_MARK(0)
+                v3_epi1<C1>(my_tmem + sl * kBlk, my_tmem + sl * kBlk + kAOff);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(bar_aready + 8u * (sl * 2 + 0));
+                PN2_MARK(1)
+            }
+            for (int sl = grp; sl < cnt; sl += 2) {
+                unsigned char *region = ring + (size_t)((it0 + sl) % R) * s.region_bytes;
+                tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 1), ph);
+                tc_fence_after();
+                PN2_MARK(2)
+                v3_epi2<C2>(my_tmem + sl * kBlk, region, row, bias2);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(bar_aready + 8u * (sl * 2 + 1));
+                PN2_MARK(3)
+            }
+            for (int sl = grp; sl < cnt; sl += 2) {
+                const int tile = blockIdx.x + (it0 + sl) * gridDim.x;
+                const int bi = tile / p.tiles_per_scene;
+                const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
+                tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 2), ph);
+                tc_fence_after();
+                PN2_MARK(4)
+                v3_epi3<NS, C3>(p, my_tmem + sl * kBlk, bi, centre0, row, bias3);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(bar_tfree + 8u * sl);
+                PN2_MARK(5)
+            }
+        }
+        if (PROF) { if (profiling) { for (int i = 0; i < 6; ++i) p.prof[i] = pc[i]; p.prof[7] = nt; } }
+    }
+#undef PN2_MARK
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// regions that fit next to the resident weights (0: the shape does not run on the pipelined kernel)
+static int v3_regions(const SaTcShape &s)
+{
+    const bool shape = (s.c1 == 64 && s.c2 == 64 && s.c3 == 128) || (s.c1 == 128 && s.c2 == 128 && s.c3 == 256);
+    if (!shape || s.w3_streamed) return 0;
+    const uint32_t fixed = 1024u + s.w1_bytes + s.w2_bytes + s.w3_bytes + s.bias_bytes + 8u * kV3Bars + 16u;
+    const uint32_t budget = 227u * 1024u;
+    if (fixed >= budget) return 0;
+    return min((int)((budget - fixed) / s.region_bytes), kV3MaxRegions);
+}
+
+template <int NS, int C1, int C2, int C3>
+static int launch_v3(const SaTcParams &q, int grid, uint32_t smem, cudaStream_t stream)
+{
+    if (q.prof) {
+        auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, true>;
+        PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kV3Threads, smem, stream>>>(q);
+    } else {
+        auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, false>;
+        PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kV3Threads, smem, stream>>>(q);
+    }
+    PN2_LAUNCH_CHECK("sa_tc_forward(pipelined)");
+    return PN2_OK;
+}
+
+
 // ---- a one-tile GEMM through the same helpers: D (128 x n) = A (128 x k) B^T (n x k) ---------------
 // Diagnostic entry point (tests/test_tc_gpu.py): isolates descriptor/layout errors from the fusion.
 __global__ void __launch_bounds__(kTcThreads)
@@ -694,6 +1124,22 @@ static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
     nstage = min(nstage, kMaxStages);
     if (const char *e = getenv("PN2_SA_TC_STAGES")) nstage = min(nstage, atoi(e));
     const uint32_t pipe_smem = pipe_fixed + (uint32_t)max(nstage, 0) * p.s.region_bytes;
+    {
+        const char *e2 = getenv("PN2_SA_TC_V2");
+        const int R = v3_regions(p.s);
+        const int T = p.s.c3 > 128 ? 2 : 4;
+        if ((!e2 || atoi(e2) != 0) && R >= T) {
+            SaTcParams q = p_in;
+            q.nslot = T;
+            q.nregion = R;
+            if (const char *er = getenv("PN2_SA_TC_V2_REGIONS")) q.nregion = max(T, min(R, atoi(er)));
+            const uint32_t smem2 = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + p.s.bias_bytes + 8u * kV3Bars + 16u +
+                                   (uint32_t)q.nregion * p.s.region_bytes;
+            const int grid = min(p.ntiles, sms);
+            return p.s.c3 == 128 ? launch_v3<NS, 64, 64, 128>(q, grid, smem2, stream)
+                                 : launch_v3<NS, 128, 128, 256>(q, grid, smem2, stream);
+        }
+    }
     const char *force = getenv("PN2_SA_TC_PIPE");
     const bool want_pipe = force ? atoi(force) != 0 : true;
     if (want_pipe && !p.s.w3_streamed && nstage >= 2) {
@@ -819,7 +1265,8 @@ extern "C" int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, i
     p.image = static_cast<const unsigned char *>(weight_image);
     p.out = out;
     p.out_table = static_cast<__nv_bfloat16 *>(out_table);
-    p.nstage = 0;
+    p.nstage = 0; p.nregion = 0; p.nslot = 0; p.blk = 0;
+    { const char *ed = getenv("PN2_SA_TC_DEBUG"); p.debug = ed ? atoi(ed) : 0; }
     p.prof = g_sa_tc_prof;
     switch (nsample) {
     case 16: return launch_sa_tc<16>(p, as_stream(stream));
