@@ -203,7 +203,8 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
         rows.append({"kernel": "ball_query_sa%d" % (lvl + 1), "bound": "hbm", "seconds": t,
                      "alg_bytes": B * (12 * (n_in + m.npoint) + 4 * m.npoint * m.nsample)})
         inv_r = 1.0 / m.radius
-        run = lambda: fused.SA_FORWARD[precision](imgs[lvl], src_xyz, cxyz, idx, table, ld, c, True, inv_r)
+        run = lambda: fused.SA_FORWARD[precision](imgs[lvl], src_xyz, cxyz, idx, table, ld, c, True, inv_r,
+                                                  raw_skip=3 if lvl == 0 else 0)
         out, out_rows = run()
         t = timeit(run)
         dims = imgs[lvl].dims

@@ -191,6 +191,21 @@ int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, int c1, int 
                       float inv_radius, const float *xyz, const float *new_xyz, const void *table,
                       const int *idx, const void *weight_image, float *out, void *out_table,
                       pn2_stream_t stream);
+/* ---- per-point half of an SA layer's first 1x1 convolution (csrc/lin_tc.cu) ---------------------
+ * Layer 1 of the SharedMLP is linear before its ReLU and only its three xyz input channels depend on the
+ * centre (pointnet2_utils.py:348-359 concatenates [xyz - centre ; features], pytorch_utils.py:11-36
+ * convolves): W1 [dxyz ; f] = W1[:, :3] dxyz + W1[:, 3:] f.  pn2_lin_tc_forward computes
+ * P = X W^T (bf16 out, f32 accumulate) once per point; pn2_sa_tc_forward is then run over the c1-wide P rows
+ * with a layer-1 weight [W1[:, :3] | I].  x: `rows` channel-last rows of pitch ld elements, f32 (16-byte
+ * aligned base, ld % 4 == 0; the first `skip` elements of a row get zero weights, so point_clouds can be
+ * read in place with skip = 3) or bf16 (ld % 8 == 0); kin = elements read per row.  c1 = 64 or 128. */
+int pn2_lin_tc_supported(int kin, int c1, int x_is_bf16);
+size_t pn2_lin_tc_weight_image_bytes(int kin, int c1);
+int pn2_lin_tc_pack_weights(int kin, int skip, int c, int c1, const float *w, int w_ld, int w_col0,
+                            void *image, pn2_stream_t stream);
+int pn2_lin_tc_forward(long long rows, int kin, int c1, const void *x, int x_is_bf16, int ld,
+                       const void *weight_image, void *out, pn2_stream_t stream);
+
 /* ---- fused feature-propagation layer on tcgen05 tensor cores ------------------------------------
  * Same chain as pn2_fp_forward_f32 (3-NN weights -> three_interpolate -> cat(skip) -> 2-layer SharedMLP),
  * inputs and outputs as bf16 channel-last rows: known_rows (b,m,c_known), skip_rows (b,n,c_skip),

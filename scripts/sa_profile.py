@@ -22,8 +22,8 @@ with torch.no_grad():
     for lvl, m in enumerate((net.sa1, net.sa2, net.sa3, net.sa4)):
         inds, cxyz = fused.fps_with_xyz(src_xyz, m.npoint)
         idx = fused.ball_query(src_xyz, cxyz, m.radius, m.nsample)
-        tab = fused.bf16_rows(table, ld, c) if table.dtype != torch.bfloat16 else table
-        run = lambda: fused.sa_forward_bf16(imgs[lvl], src_xyz, cxyz, idx, tab, tab.shape[2], c, True, 1.0 / m.radius)
+        skip = 3 if lvl == 0 else 0
+        run = lambda: fused.sa_forward_bf16(imgs[lvl], src_xyz, cxyz, idx, table, ld, c, True, 1.0 / m.radius, raw_skip=skip)
         run()
         check(lib.pn2_debug_sa_tc_profile(ptr(prof)), "prof")
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,12 +31,12 @@ with torch.no_grad():
         check(lib.pn2_debug_sa_tc_profile(None), "prof")
         pr = prof.cpu().numpy()
         tiles = max(int(pr[7]), 1)
-        print("SA%d: %.1f us, CTA0 tiles %d" % (lvl + 1, 1e3 * s.elapsed_time(e), tiles))
+        print("SA%d: %.1f us (pack / per-point GEMM + fused kernel), CTA0 tiles %d" % (lvl + 1, 1e3 * s.elapsed_time(e), tiles))
         if V2:
             f = lambda a, names: {n: int(v / tiles) for n, v in zip(names, a)}
             print("  epilogue cycles/tile:", f(pr[0:6], ["wait d1", "e1", "wait d2", "e2", "wait d3", "e3"]), "sum", int(pr[:6].sum() / tiles))
             print("  issuer A cycles/tile:", f(pr[8:11], ["wait full", "wait tfree", "issue L1"]))
-            print("  issuer B cycles/tile:", f(pr[11:15], ["wait a1", "issue L2", "wait a2", "issue L3"]))
+            print("  issuers B, C cycles/tile:", f(pr[11:15], ["wait a1", "issue L2", "wait a2", "issue L3"]))
             print("  gather   cycles/tile:", f(pr[16:19], ["wait empty", "issue gathers", "xyz chunk"]))
         else:
             print("  consumer cycles/tile:", {n: int(v / tiles) for n, v in zip(names, pr[:7])}, "sum", int(pr[:7].sum() / tiles))

@@ -64,6 +64,10 @@ _PROTOTYPES = {
     "pn2_sa_tc_pack_rows": (_i, [_i, _i, _i, _p, ctypes.c_longlong, _i, _p, _p]),
     "pn2_sa_tc_pack_channels": (_i, [_i, _i, _i, _p, _p, _p]),
     "pn2_sa_tc_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_lin_tc_supported": (_i, [_i, _i, _i]),
+    "pn2_lin_tc_weight_image_bytes": (c_size_t, [_i, _i]),
+    "pn2_lin_tc_pack_weights": (_i, [_i, _i, _i, _i, _p, _i, _i, _p, _p]),
+    "pn2_lin_tc_forward": (_i, [ctypes.c_longlong, _i, _i, _p, _i, _i, _p, _p, _p]),
     "pn2_fp_tc_supported": (_i, [_i, _i, _i, _i]),
     "pn2_fp_tc_weight_image_bytes": (c_size_t, [_i, _i, _i, _i]),
     "pn2_fp_tc_pack_weights": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),

@@ -97,16 +97,16 @@ class Pointnet2Backbone(nn.Module):
                 src = cxyz[lvl]
 
         feats, rows = [], []
-        src_xyz, table, ld, c = xyz, pc[..., 3:], W, W - 3
+        src_xyz, table, ld, c, skip = xyz, pc[..., 3:], W, W - 3, 3
         for lvl, m in enumerate(sas):
             main.wait_event(ready[lvl])
             idx = _fused.ball_query(src_xyz, cxyz[lvl], m.radius, m.nsample)
             inv_r = 1.0 / m.radius if m.normalize_xyz else 1.0
             out, out_rows = _fused.SA_FORWARD[self.precision](imgs[lvl], src_xyz, cxyz[lvl], idx, table, ld, c,
-                                                             m.use_xyz, inv_r)
+                                                             m.use_xyz, inv_r, raw_skip=skip)
             feats.append(out)
             rows.append(out_rows)
-            src_xyz, table, ld, c = cxyz[lvl], out_rows, out_rows.shape[2], out_rows.shape[2]
+            src_xyz, table, ld, c, skip = cxyz[lvl], out_rows, out_rows.shape[2], out_rows.shape[2], 0
             data_dict["sa%d_inds" % (lvl + 1)] = inds[lvl]
             data_dict["sa%d_xyz" % (lvl + 1)] = cxyz[lvl]
             data_dict["sa%d_features" % (lvl + 1)] = out

@@ -642,18 +642,19 @@ sa_tc_pipe_kernel(const SaTcParams p)
 // Here T tiles (T = 512 / TMEM columns per tile: 4 at SA1, 2 for the 256-wide layers) are in flight at
 // once, each in its own shared-memory region and TMEM slot, and the roles are separate warps that only
 // meet at mbarriers:
-//   warps 0-3 / 4-7  two epilogue groups; group g owns the slots s = g (mod 2).  Per wave of T tiles a
-//                    group runs E1 of its slots, then E2, then E3.
-//   warp 8           issues layer 1 of tile after tile (needs: region gathered, slot's previous E3 done)
-//   warp 9           issues layers 2 and 3 in wave order
+//   warps 0-3 / 4-7  two epilogue groups; group g takes every other tile (it = g, g + 2, ...) and runs its
+//                    three epilogues in the skewed order E1(k), E3(k-1), E2(k)
+//   warps 8, 9, 10   one issuer per layer, each walking the tiles in order (layer 1 needs: region gathered,
+//                    slot's previous E3 done; layers 2 / 3 need the epilogue before them)
 //   warps 12-15      gather, up to R - T tiles ahead of the tensor core (R regions, as many as fit)
-// Every dependency points backwards in the wave order (R >= T), so the schedule cannot deadlock.
+// Every wait is on an event that only depends on earlier tiles or earlier tasks of the same tile (R >= T),
+// so the schedule cannot deadlock; no role ever waits behind another tile's later layer.
 // Layer widths are compile-time, so the epilogues are straight-line code.  Layer-1 activations never
 // touch shared memory: E1 writes them as packed bf16 back into TMEM and layer 2 reads its A operand from
 // there (tcgen05.mma with A in TMEM), which removes a swizzled store pass, a generic->async proxy fence
 // and a quarter of the shared-memory operand traffic per tile.
 constexpr int kV3EpiThreads = 256;
-constexpr int kV3WarpA = 8, kV3WarpB = 9, kV3ProdWarp0 = 12;   // warps 10, 11 idle (registers are allocated per 4 warps)
+constexpr int kV3WarpA = 8, kV3WarpB = 9, kV3WarpC = 10, kV3ProdWarp0 = 12;   // warp 11 idle (registers are allocated per 4 warps)
 constexpr int kV3Producers = 128;
 constexpr int kV3Threads = 512;
 constexpr int kV3MaxRegions = 8, kV3MaxSlots = 4;
@@ -683,14 +684,19 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // E1: D1 (fp32, this thread's row) -> ReLU -> bf16 pairs -> TMEM columns of the layer-2 A operand
 template <int C1>
-__device__ __forceinline__ void v3_epi1(uint32_t d_taddr, uint32_t a_taddr)
+__device__ __forceinline__ void v3_epi1(uint32_t d_taddr, uint32_t a_taddr, int debug)
 {
 #pragma unroll
     for (int c0 = 0; c0 < C1; c0 += 64) {
         uint32_t va[32], vb[32];
+        if (debug & 16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0u;
+        } else {
         tmem_ld32_issue(d_taddr + c0, va);
         tmem_ld32_issue(d_taddr + c0 + 32, vb);
         tmem_ld_wait();
+        }
         uint32_t pa[16], pb[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -705,16 +711,21 @@ __device__ __forceinline__ void v3_epi1(uint32_t d_taddr, uint32_t a_taddr)
 
 // E2: D2 + bias -> ReLU -> bf16 -> K-major 128B-swizzled rows of the region (the layer-3 B operand)
 template <int C2>
-__device__ __forceinline__ void v3_epi2(uint32_t d_taddr, unsigned char *region, int row, const float *bias2)
+__device__ __forceinline__ void v3_epi2(uint32_t d_taddr, unsigned char *region, int row, const float *bias2, int debug)
 {
     unsigned char *row_base = region + row * 128;
     const uint32_t r7 = (uint32_t)(row & 7);
 #pragma unroll
     for (int c0 = 0; c0 < C2; c0 += 64) {
         uint32_t v[2][32];
+        if (debug & 16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[0][j] = v[1][j] = 0u;
+        } else {
         tmem_ld32_issue(d_taddr + c0, v[0]);
         tmem_ld32_issue(d_taddr + c0 + 32, v[1]);
         tmem_ld_wait();
+        }
         unsigned char *tile_base = row_base + (c0 / 64) * (kTile * 128);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -748,9 +759,14 @@ __device__ __forceinline__ void v3_epi3(const SaTcParams &p, uint32_t d_taddr, i
 #pragma unroll
         for (int q0 = 0; q0 < kTile; q0 += 64) {
             uint32_t v[2][32];
+            if (p.debug & 16) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[0][j] = v[1][j] = 0u;
+            } else {
             tmem_ld32_issue(d_taddr + mt * kTile + q0, v[0]);
             tmem_ld32_issue(d_taddr + mt * kTile + q0 + 32, v[1]);
             tmem_ld_wait();
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int col = q0 + h * 32;
@@ -766,8 +782,10 @@ __device__ __forceinline__ void v3_epi3(const SaTcParams &p, uint32_t d_taddr, i
                     if ((col + 32) % NS == 0) {
                         const int cl = col / NS;
                         const float o = fmaxf(run + bias, 0.f);
+                        if (!(p.debug & 8) || o == 12345.f) {
                         out[cl] = o;
                         if (out_t) out_t[(size_t)cl * C3] = __float2bfloat16_rn(o);
+                        }
                         run = -3.0e38f;
                     }
                 } else {
@@ -787,7 +805,7 @@ __device__ __forceinline__ void v3_epi3(const SaTcParams &p, uint32_t d_taddr, i
     }
 }
 
-template <int NS, int C1, int C2, int C3, bool PROF>
+template <int NS, int C1, int C2, int C3, int NCHUNK, bool PROF>
 __global__ void __launch_bounds__(kV3Threads, 1)
 sa_tc_v3_kernel(const SaTcParams p)
 {
@@ -821,7 +839,7 @@ sa_tc_v3_kernel(const SaTcParams p)
         for (int i = tid; i < C2 + C3; i += kV3Threads) bias2[i] = __ldg(bsrc + i);
         if (tid == 0) {
             for (int i = 0; i < kV3MaxRegions; ++i) {
-                tc_mbar_init(bar_full + 8u * i, 2 * kV3Producers);   // cp.async completion + explicit arrival per gather thread
+                tc_mbar_init(bar_full + 8u * i, kV3Producers / 32);  // one arrival per gather warp once its copies have landed
                 tc_mbar_init(bar_empty + 8u * i, 1);                 // tcgen05.commit after the tile's last MMA
             }
             for (int i = 0; i < 3 * kV3MaxSlots; ++i) tc_mbar_init(bar_dfull + 8u * i, 1);    // tcgen05.commit
@@ -844,76 +862,103 @@ sa_tc_v3_kernel(const SaTcParams p)
 
     if (warp >= kV3ProdWarp0) {
         // ===== gather warps: warp pw copies rows pw*32 .. pw*32+31 of the tile =====
-        // A cp.async instruction covers two whole rows (lanes 0-15 / 16-31 take 16 consecutive 16-byte chunks
-        // each), so it touches the 5-6 cache lines those rows occupy instead of 16-32 lines of as many rows;
-        // the chunks left over (row_elems/8 mod 16) are copied 32/rem rows at a time.
+        // The 32 x NCHUNK 16-byte chunks of the warp's rows are copied in row-major order, 32 consecutive
+        // chunks per cp.async instruction, so an instruction touches the few cache lines of 2-4 whole rows
+        // instead of one sector in each of 16-32 rows.  Which (row, chunk) a lane copies in step j and where
+        // it lands in the swizzled operand do not depend on the tile: both are computed once, so a step is
+        // shuffle (the row's neighbour index) + address + cp.async, all steps independent of each other.
+        constexpr int K0 = ((NCHUNK * 8 + 8 + 15) / 16) * 16;
+        constexpr int kRowBytes = NCHUNK * 16;
+        // cp.async groups in flight behind the one being issued: a tile is published `lag` iterations after its
+        // copies were issued; only as far ahead as there are spare regions (a tile must be published before the
+        // gather blocks on a region that tile's successors hold)
+        const int lag = R - T >= 2 ? 2 : (R - T >= 1 ? 1 : 0);
         const int pw = warp - kV3ProdWarp0;
         const int myrow = pw * 32 + lane;
-        const int nchunk = s.row_elems / 8, xchunk = nchunk, k0chunks = s.k0 / 8;
-        const int nfull16 = nchunk & ~15, rem = nchunk & 15;
+        uint32_t item_off[NCHUNK];       // bits 0-17: byte offset in the region, bits 24-28: row within the warp's 32
+        uint32_t item_src[NCHUNK];       // byte offset of the chunk within its table row
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            const int i = lane + 32 * j, rr = i / NCHUNK, ch = i - rr * NCHUNK;
+            item_off[j] = kop_chunk_off(kTile, K0, pw * 32 + rr, ch) | ((uint32_t)rr << 24);
+            item_src[j] = (uint32_t)ch * 16u;
+        }
+        const uint32_t x_off = kop_chunk_off(kTile, K0, myrow, NCHUNK);
         const bool profiling = prof_cta && tid == kV3ProdWarp0 * 32;
         if (PROF) { if (profiling) tprev = clock64(); }
-        int nb_next = 0;
-        if (nt > 0) {
-            const int t0 = blockIdx.x, bi0 = t0 / p.tiles_per_scene;
-            nb_next = __ldg(p.idx + (size_t)bi0 * p.npoint * NS + (t0 - bi0 * p.tiles_per_scene) * kTile + myrow);
-        }
+        // Global-load latencies are taken off the per-tile critical path: the neighbour index of this lane's row
+        // is fetched two tiles ahead, the row's and the centre's coordinates (addressed by that index) one tile
+        // ahead.
+        auto load_idx = [&](int it_) -> int {
+            if (it_ >= nt) return 0;
+            const int t_ = blockIdx.x + it_ * gridDim.x, b_ = t_ / p.tiles_per_scene;
+            return __ldg(p.idx + (size_t)b_ * p.npoint * NS + (t_ - b_ * p.tiles_per_scene) * kTile + myrow);
+        };
+        float px[3] = {0.f, 0.f, 0.f}, cx[3] = {0.f, 0.f, 0.f};
+        auto load_xyz = [&](int it_, int nb_) {
+            if (it_ >= nt) return;
+            const int t_ = blockIdx.x + it_ * gridDim.x, b_ = t_ / p.tiles_per_scene;
+            const int r0_ = (t_ - b_ * p.tiles_per_scene) * kTile;
+            const float *pp = p.xyz + ((size_t)b_ * p.n + nb_) * 3;
+            const float *cc = p.new_xyz + ((size_t)b_ * p.npoint + (r0_ + myrow) / NS) * 3;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { px[a] = __ldg(pp + a); cx[a] = __ldg(cc + a); }
+        };
+        int nb_cur = load_idx(0), nb_next = load_idx(1);
+        if (p.debug & 32) nb_cur = myrow;
+        load_xyz(0, nb_cur);
         for (int it = 0; it < nt; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int rg = it % R, u = it / R;
-            const int nb = nb_next;
-            if (it + 1 < nt) {
-                const int t1 = tile + gridDim.x, bn = t1 / p.tiles_per_scene;
-                nb_next = __ldg(p.idx + (size_t)bn * p.npoint * NS + (t1 - bn * p.tiles_per_scene) * kTile + myrow);
-            }
+            const int nb = nb_cur;
             const int bi = tile / p.tiles_per_scene;
-            const int row0 = (tile - bi * p.tiles_per_scene) * kTile;
-            // recentred, normalised xyz of this lane's row (loads issued before the wait)
-            const float *pp = p.xyz + ((size_t)bi * p.n + nb) * 3;
-            const float *cc = p.new_xyz + ((size_t)bi * p.npoint + (row0 + myrow) / NS) * 3;
+            // recentred, normalised xyz of this lane's row, from the coordinates loaded during the previous tile
             float h[3], l[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const float d = __fmul_rn(__fsub_rn(__ldg(pp + a), __ldg(cc + a)), p.inv_radius);
+                const float d = __fmul_rn(__fsub_rn(px[a], cx[a]), p.inv_radius);
                 h[a] = __bfloat162float(__float2bfloat16_rn(d));
                 l[a] = d - h[a];
             }
+            nb_cur = (p.debug & 32) ? myrow : nb_next;
+            load_xyz(it + 1, nb_cur);
+            nb_next = load_idx(it + 2);
             if (u > 0) tc_mbar_wait(bar_empty + 8u * rg, (u - 1) & 1);
             PN2_MARK(0)
             unsigned char *region = ring + (size_t)rg * s.region_bytes;
             const uint32_t a_base = smem_u32(region);
-            const __nv_bfloat16 *tab = p.table + (size_t)bi * p.n * s.row_elems;
+            const unsigned char *tab = reinterpret_cast<const unsigned char *>(p.table) + (size_t)bi * p.n * kRowBytes;
             if (!(p.debug & 1)) {
-                for (int cb = 0; cb < nfull16; cb += 16) {
-#pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int rr = 2 * i + (lane >> 4);
-                        const int nbr = __shfl_sync(0xffffffffu, nb, rr);
-                        const int ch = cb + (lane & 15);
-                        cp_async16(a_base + kop_chunk_off(kTile, s.k0, pw * 32 + rr, ch),
-                                   tab + (size_t)nbr * s.row_elems + ch * 8);
-                    }
-                }
-                if (rem) {
-                    for (int j = lane; j < 32 * rem; j += 32) {
-                        const int rr = j / rem, ch = nfull16 + (j - rr * rem);
-                        const int nbr = __shfl_sync(0xffffffffu, nb, rr);
-                        cp_async16(a_base + kop_chunk_off(kTile, s.k0, pw * 32 + rr, ch),
-                                   tab + (size_t)nbr * s.row_elems + ch * 8);
-                    }
+#pragma unroll
+                for (int j = 0; j < NCHUNK; ++j) {
+                    const int nbr = __shfl_sync(0xffffffffu, nb, (int)(item_off[j] >> 24));
+                    cp_async16(a_base + (item_off[j] & 0xffffffu), tab + (size_t)nbr * kRowBytes + item_src[j]);
                 }
             }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8u * rg) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
             PN2_MARK(1)
-            *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, myrow, xchunk)) =
+            *reinterpret_cast<uint4 *>(region + x_off) =
                 make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], l[0]), pack_bf16(l[1], l[2]), pack_bf16(1.f, 1.f));
-            for (int ch = xchunk + 1; ch < k0chunks; ++ch)
-                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, myrow, ch)) = make_uint4(0u, 0u, 0u, 0u);
-            fence_proxy_async();
-            tc_mbar_arrive(bar_full + 8u * rg);
+#pragma unroll
+            for (int ch = NCHUNK + 1; ch < K0 / 8; ++ch)
+                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, K0, myrow, ch)) = make_uint4(0u, 0u, 0u, 0u);
+            // the tile issued kLag iterations ago has landed by now: publish it (one arrival per warp)
+            if (it >= lag) {
+                if (lag == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                else if (lag == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc_mbar_arrive(bar_full + 8u * ((it - lag) % R));
+            }
             PN2_MARK(2)
         }
+        // drain: the last `lag` tiles
         cp_async_wait_all();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0)
+            for (int it = max(nt - lag, 0); it < nt; ++it) tc_mbar_arrive(bar_full + 8u * (it % R));
         if (PROF) { if (profiling) for (int i = 0; i < 3; ++i) p.prof[16 + i] = pc[i]; }
     } else if (warp == kV3WarpA) {
         // ===== layer-1 issuer =====
@@ -938,91 +983,112 @@ sa_tc_v3_kernel(const SaTcParams p)
         }
         if (PROF) { if (profiling) for (int i = 0; i < 3; ++i) p.prof[8 + i] = pc[i]; }
     } else if (warp == kV3WarpB) {
-        // ===== layer-2 / layer-3 issuer =====
-        const uint32_t idesc2 = umma_idesc(kTile, C2), idesc3 = umma_idesc(128, kTile);
-        const uint32_t w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
-        const uint64_t dw2 = smem_desc(w2_base, 1024u, kSw128);
+        // ===== layer-2 issuer (A operand = the bf16 activations E1 left in TMEM) =====
+        const uint32_t idesc2 = umma_idesc(kTile, C2);
+        const uint64_t dw2 = smem_desc(smem_u32(w2s), 1024u, kSw128);
         const uint32_t elected = elect_one();
         const bool profiling = prof_cta && lane == 0;
         if (PROF) { if (profiling) tprev = clock64(); }
-        for (int w = 0, it0 = 0; it0 < nt; ++w, it0 += T) {
-            const int cnt = min(T, nt - it0);
-            for (int sl = 0; sl < cnt; ++sl) {
-                tc_mbar_wait(bar_aready + 8u * (sl * 2 + 0), w & 1);           // A1 in TMEM, D1 drained
-                PN2_MARK(0)
-                tc_fence_after();
-                const uint32_t d = tmem + sl * kBlk;
+        for (int it = 0; it < nt; ++it) {
+            const int sl = it % T, w = it / T;
+            tc_mbar_wait(bar_aready + 8u * (sl * 2 + 0), w & 1);               // A1 in TMEM, D1 drained
+            PN2_MARK(0)
+            tc_fence_after();
+            const uint32_t d = tmem + sl * kBlk;
 #pragma unroll
-                for (int ks = 0; ks < C1 / 16; ++ks)
-                    if (elected)
-                        umma_bf16_ta(d, d + kAOff + ks * 8, dw2 + (uint64_t)((ks >> 2) * (C2 * 8) + (ks & 3) * 2), idesc2,
-                                     (uint32_t)(ks != 0));
-                if (elected) umma_commit(bar_dfull + 8u * (sl * 3 + 1));
-                __syncwarp();
-                PN2_MARK(1)
-            }
-            for (int sl = 0; sl < cnt; ++sl) {
-                const int rg = (it0 + sl) % R;
-                tc_mbar_wait(bar_aready + 8u * (sl * 2 + 1), w & 1);           // A2 in the region, D2 drained
-                PN2_MARK(2)
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(ring + (size_t)rg * s.region_bytes);
-#pragma unroll
-                for (int mt = 0; mt < C3 / 128; ++mt)
-                    issue_gemm(tmem + sl * kBlk + mt * kTile, w3_base, C3, mt * 128, a_base, kTile, 0, C2, idesc3, elected);
-                if (elected) {
-                    umma_commit(bar_dfull + 8u * (sl * 3 + 2));
-                    umma_commit(bar_empty + 8u * rg);                           // region free for the gather warps
-                }
-                __syncwarp();
-                PN2_MARK(3)
-            }
+            for (int ks = 0; ks < C1 / 16; ++ks)
+                if (elected)
+                    umma_bf16_ta(d, d + kAOff + ks * 8, dw2 + (uint64_t)((ks >> 2) * (C2 * 8) + (ks & 3) * 2), idesc2,
+                                 (uint32_t)(ks != 0));
+            if (elected) umma_commit(bar_dfull + 8u * (sl * 3 + 1));
+            __syncwarp();
+            PN2_MARK(1)
         }
-        if (PROF) { if (profiling) for (int i = 0; i < 4; ++i) p.prof[11 + i] = pc[i]; }
+        if (PROF) { if (profiling) for (int i = 0; i < 2; ++i) p.prof[11 + i] = pc[i]; }
+    } else if (warp == kV3WarpC) {
+        // ===== layer-3 issuer (operands swapped: channels on the TMEM lanes) =====
+        const uint32_t idesc3 = umma_idesc(128, kTile);
+        const uint32_t w3_base = smem_u32(w3s);
+        const uint32_t elected = elect_one();
+        const bool profiling = prof_cta && lane == 0;
+        if (PROF) { if (profiling) tprev = clock64(); }
+        for (int it = 0; it < nt; ++it) {
+            const int sl = it % T, w = it / T, rg = it % R;
+            tc_mbar_wait(bar_aready + 8u * (sl * 2 + 1), w & 1);               // A2 in the region, D2 drained
+            PN2_MARK(0)
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(ring + (size_t)rg * s.region_bytes);
+#pragma unroll
+            for (int mt = 0; mt < C3 / 128; ++mt)
+                issue_gemm(tmem + sl * kBlk + mt * kTile, w3_base, C3, mt * 128, a_base, kTile, 0, C2, idesc3, elected);
+            if (elected) {
+                umma_commit(bar_dfull + 8u * (sl * 3 + 2));
+                umma_commit(bar_empty + 8u * rg);                               // region free for the gather warps
+            }
+            __syncwarp();
+            PN2_MARK(1)
+        }
+        if (PROF) { if (profiling) for (int i = 0; i < 2; ++i) p.prof[13 + i] = pc[i]; }
     } else if (warp < kV3EpiThreads / 32) {
-        // ===== epilogue groups: group g = warp / 4 owns slots g, g + 2; warp w works on TMEM lanes 32*(w%4).. =====
+        // ===== epilogue groups: group g = warp / 4 takes the tiles it = g, g + 2, ...; warp w works on TMEM lanes
+        // 32*(w%4)..  With four slots a group has two tiles in flight and runs E1(k), E3(k-1), E2(k): each
+        // task's input was produced a whole task earlier, so the group rarely waits.  With two slots (one per
+        // group) the order is E1, E2, E3 of one tile.
         const int quarter = warp & 3, grp = warp >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t my_tmem = tmem + ((uint32_t)(quarter * 32) << 16);
         const bool profiling = prof_cta && tid == 0;
         if (PROF) { if (profiling) tprev = clock64(); }
-        for (int w = 0, it0 = 0; it0 < nt; ++w, it0 += T) {
-            const int cnt = min(T, nt - it0);
-            const uint32_t ph = (uint32_t)(w & 1);
-            for (int sl = grp; sl < cnt; sl += 2) {
-                tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 0), ph);
-                tc_fence_after();
-                PN2_MARK(0)
-                v3_epi1<C1>(my_tmem + sl * kBlk, my_tmem + sl * kBlk + kAOff);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(bar_aready + 8u * (sl * 2 + 0));
-                PN2_MARK(1)
+        const int nk = nt > grp ? (nt - grp + 1) / 2 : 0;
+        auto epi1 = [&](int it) {
+            const int sl = it % T;
+            tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 0), (uint32_t)((it / T) & 1));
+            tc_fence_after();
+            PN2_MARK(0)
+            v3_epi1<C1>(my_tmem + sl * kBlk, my_tmem + sl * kBlk + kAOff, p.debug);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(bar_aready + 8u * (sl * 2 + 0));
+            PN2_MARK(1)
+        };
+        auto epi2 = [&](int it) {
+            const int sl = it % T;
+            unsigned char *region = ring + (size_t)(it % R) * s.region_bytes;
+            tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 1), (uint32_t)((it / T) & 1));
+            tc_fence_after();
+            PN2_MARK(2)
+            v3_epi2<C2>(my_tmem + sl * kBlk, region, row, bias2, p.debug);
+            tc_fence_before();
+            if (!(p.debug & 4)) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(bar_aready + 8u * (sl * 2 + 1));
+            PN2_MARK(3)
+        };
+        auto epi3 = [&](int it) {
+            const int sl = it % T;
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int bi = tile / p.tiles_per_scene;
+            const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
+            tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 2), (uint32_t)((it / T) & 1));
+            tc_fence_after();
+            PN2_MARK(4)
+            v3_epi3<NS, C3>(p, my_tmem + sl * kBlk, bi, centre0, row, bias3);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(bar_tfree + 8u * sl);
+            PN2_MARK(5)
+        };
+        if (T >= 4) {
+            for (int k = 0; k <= nk; ++k) {
+                if (k < nk) epi1(2 * k + grp);
+                if (k >= 1) epi3(2 * (k - 1) + grp);
+                if (k < nk) epi2(2 * k + grp);
             }
-            for (int sl = grp; sl < cnt; sl += 2) {
-                unsigned char *region = ring + (size_t)((it0 + sl) % R) * s.region_bytes;
-                tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 1), ph);
-                tc_fence_after();
-                PN2_MARK(2)
-                v3_epi2<C2>(my_tmem + sl * kBlk, region, row, bias2);
-                tc_fence_before();
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(bar_aready + 8u * (sl * 2 + 1));
-                PN2_MARK(3)
-            }
-            for (int sl = grp; sl < cnt; sl += 2) {
-                const int tile = blockIdx.x + (it0 + sl) * gridDim.x;
-                const int bi = tile / p.tiles_per_scene;
-                const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
-                tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 2), ph);
-                tc_fence_after();
-                PN2_MARK(4)
-                v3_epi3<NS, C3>(p, my_tmem + sl * kBlk, bi, centre0, row, bias3);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc_mbar_arrive(bar_tfree + 8u * sl);
-                PN2_MARK(5)
+        } else {
+            for (int k = 0; k < nk; ++k) {
+                epi1(2 * k + grp);
+                epi2(2 * k + grp);
+                epi3(2 * k + grp);
             }
         }
         if (PROF) { if (profiling) { for (int i = 0; i < 6; ++i) p.prof[i] = pc[i]; p.prof[7] = nt; } }
@@ -1036,7 +1102,9 @@ sa_tc_v3_kernel(const SaTcParams p)
 // regions that fit next to the resident weights (0: the shape does not run on the pipelined kernel)
 static int v3_regions(const SaTcShape &s)
 {
-    const bool shape = (s.c1 == 64 && s.c2 == 64 && s.c3 == 128) || (s.c1 == 128 && s.c2 == 128 && s.c3 == 256);
+    const int nchunk = s.row_elems / 8;
+    const bool shape = (s.c1 == 64 && s.c2 == 64 && s.c3 == 128 && (nchunk == 8 || nchunk == 17)) ||
+                       (s.c1 == 128 && s.c2 == 128 && s.c3 == 256 && (nchunk == 16 || nchunk == 17));
     if (!shape || s.w3_streamed) return 0;
     const uint32_t fixed = 1024u + s.w1_bytes + s.w2_bytes + s.w3_bytes + s.bias_bytes + 8u * kV3Bars + 16u;
     const uint32_t budget = 227u * 1024u;
@@ -1044,15 +1112,17 @@ static int v3_regions(const SaTcShape &s)
     return min((int)((budget - fixed) / s.region_bytes), kV3MaxRegions);
 }
 
-template <int NS, int C1, int C2, int C3>
+template <int NS, int C1, int C2, int C3, int NCHUNK>
 static int launch_v3(const SaTcParams &q, int grid, uint32_t smem, cudaStream_t stream)
 {
-    if (q.prof) {
-        auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, true>;
+    // the phase profile is compiled for the bench shapes only
+    constexpr bool kHasProf = (NS == 64 && C3 == 128) || (NS == 32 && NCHUNK == 17 && C3 == 256) || (NS == 16 && NCHUNK == 16);
+    if (kHasProf && q.prof) {
+        auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, NCHUNK, kHasProf>;
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kV3Threads, smem, stream>>>(q);
     } else {
-        auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, false>;
+        auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, NCHUNK, false>;
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kV3Threads, smem, stream>>>(q);
     }
@@ -1060,6 +1130,21 @@ static int launch_v3(const SaTcParams &q, int grid, uint32_t smem, cudaStream_t 
     return PN2_OK;
 }
 
+// the instantiated (layer widths, table row width) combinations: SA1 / SA2-4 shapes of the backbone over
+// feature rows (17 chunks = 129..136 channels) or over the per-point layer-1 rows of lin_tc.cu (8 / 16 chunks)
+template <int NS>
+static int dispatch_v3(const SaTcParams &q, int grid, uint32_t smem, cudaStream_t stream)
+{
+    const int nchunk = q.s.row_elems / 8;
+    if (q.s.c3 == 128) {
+        if (nchunk == 8) return launch_v3<NS, 64, 64, 128, 8>(q, grid, smem, stream);
+        if (nchunk == 17) return launch_v3<NS, 64, 64, 128, 17>(q, grid, smem, stream);
+    } else {
+        if (nchunk == 16) return launch_v3<NS, 128, 128, 256, 16>(q, grid, smem, stream);
+        if (nchunk == 17) return launch_v3<NS, 128, 128, 256, 17>(q, grid, smem, stream);
+    }
+    return PN2_ERR_INVALID_ARGUMENT;
+}
 
 // ---- a one-tile GEMM through the same helpers: D (128 x n) = A (128 x k) B^T (n x k) ---------------
 // Diagnostic entry point (tests/test_tc_gpu.py): isolates descriptor/layout errors from the fusion.
@@ -1128,7 +1213,7 @@ static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
         const char *e2 = getenv("PN2_SA_TC_V2");
         const int R = v3_regions(p.s);
         const int T = p.s.c3 > 128 ? 2 : 4;
-        if ((!e2 || atoi(e2) != 0) && R >= T) {
+        if ((!e2 || atoi(e2) != 0) && R >= T && NS <= 64) {
             SaTcParams q = p_in;
             q.nslot = T;
             q.nregion = R;
@@ -1136,8 +1221,7 @@ static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
             const uint32_t smem2 = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + p.s.bias_bytes + 8u * kV3Bars + 16u +
                                    (uint32_t)q.nregion * p.s.region_bytes;
             const int grid = min(p.ntiles, sms);
-            return p.s.c3 == 128 ? launch_v3<NS, 64, 64, 128>(q, grid, smem2, stream)
-                                 : launch_v3<NS, 128, 128, 256>(q, grid, smem2, stream);
+            return dispatch_v3<NS>(q, grid, smem2, stream);
         }
     }
     const char *force = getenv("PN2_SA_TC_PIPE");

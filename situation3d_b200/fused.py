@@ -4,6 +4,8 @@ Nothing here computes on the host: it reads module parameters, folds eval-mode B
 into the 1x1-conv weights (W' = W*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)),
 hands them to the C ABI's pack functions and launches the fused kernels on the current stream.
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -56,6 +58,7 @@ class MlpImage:
         self.folded = None
         self.f32_only = True
         self._f32_alt = None
+        self._split = {}
 
     def get(self, mlp, precision, kind="sa"):
         key = (precision, kind) + _mlp_state_key(mlp)
@@ -74,7 +77,16 @@ class MlpImage:
                 self.f32_only = precision != "bf16"
             self.key, self.dims, self.folded = key, dims, folded
             self._f32_alt = None
+            self._split = {}
         return self
+
+    def split(self, kin, skip, x_is_bf16):
+        """Images of the split first layer (csrc/lin_tc.cu): (lin image, SA image over the c1-wide P rows), or
+        None when the shapes are outside the kernels.  Cached per input layout."""
+        key = (kin, skip, x_is_bf16)
+        if key not in self._split:
+            self._split[key] = _pack_split(self.dims, self.folded, kin, skip, x_is_bf16)
+        return self._split[key]
 
 
 def _pack_f32(dims, folded):
@@ -108,6 +120,53 @@ def _pack_bf16(dims, folded):
         check(lib.pn2_sa_tc_pack_weights(c, c1, c2, c3, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3),
                                          ptr(image), stream_ptr()), "sa_tc_pack_weights")
     return image
+
+
+def _pack_split(dims, folded, kin, skip, x_is_bf16):
+    """W1 [xyz ; f] = W1[:, :3] xyz + W1[:, 3:] f: the feature half becomes a per-point row GEMM (lin image),
+    the SA kernel keeps the xyz / bias columns and an identity block over the c1-wide result."""
+    if len(folded) != 3:
+        return None
+    c, c1, c2, c3 = dims[0] - 3, dims[1], dims[2], dims[3]
+    if not lib.pn2_lin_tc_supported(kin, c1, 1 if x_is_bf16 else 0):
+        return None
+    sa_bytes = lib.pn2_sa_tc_weight_image_bytes(c1, c1, c2, c3)
+    lin_bytes = lib.pn2_lin_tc_weight_image_bytes(kin, c1)
+    if sa_bytes == 0 or lin_bytes == 0:
+        return None
+    (w1, b1), (w2, b2), (w3, b3) = folded
+    dev = w1.device
+    lin_image = torch.empty(lin_bytes, dtype=torch.uint8, device=dev)
+    sa_image = torch.empty(sa_bytes, dtype=torch.uint8, device=dev)
+    w1p = torch.cat([w1[:, :3], torch.eye(c1, dtype=torch.float32, device=dev)], dim=1).contiguous()
+    with torch.cuda.device(dev):
+        check(lib.pn2_lin_tc_pack_weights(kin, skip, c, c1, ptr(w1), c + 3, 3, ptr(lin_image), stream_ptr()),
+              "lin_tc_pack_weights")
+        check(lib.pn2_sa_tc_pack_weights(c1, c1, c2, c3, ptr(w1p), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3),
+                                         ptr(sa_image), stream_ptr()), "sa_tc_pack_weights")
+    return lin_image, sa_image
+
+
+def _rup(v, m):
+    return (v + m - 1) // m * m
+
+
+def split_first_layer(c, c1):
+    """True when gathering c1-wide per-point results is cheaper than gathering the c-wide feature rows
+    (layer-1 K of the fused kernel: c1 + 16 against round_up(round_up(c, 8) + 8, 16))."""
+    import os
+    if os.environ.get("PN2_SA_SPLIT", "1") == "0":
+        return False
+    return c1 in (64, 128) and c1 + 16 < _rup(_rup(c, 8) + 8, 16)
+
+
+def lin_rows(lin_image, x, base_ptr, rows, kin, c1, x_is_bf16, ld):
+    """P (rows, c1) bf16 = X W^T over channel-last rows (pn2_lin_tc_forward)."""
+    out = torch.empty((rows, c1), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.pn2_lin_tc_forward(rows, kin, c1, base_ptr, 1 if x_is_bf16 else 0, ld, ptr(lin_image), ptr(out),
+                                     stream_ptr()), "lin_tc_forward")
+    return out
 
 
 def _pack_fp_bf16(dims, folded):
@@ -182,7 +241,7 @@ def three_nn(unknown, known):
     return dist2, idx
 
 
-def sa_forward_f32(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True):
+def sa_forward_f32(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True, raw_skip=0):
     """Fused QueryAndGroup-gather + SharedMLP + max-pool (pn2_sa_forward_f32).
     table: tensor whose data pointer is the first feature of row (0,0); ld = row pitch in floats."""
     B, N, _ = xyz.shape
@@ -227,7 +286,7 @@ def _f32_rows(rows):
     return rows if rows is None or rows.dtype == torch.float32 else rows.float()
 
 
-def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True):
+def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True, raw_skip=0):
     """Fused SA layer on tcgen05 (pn2_sa_tc_forward).  ``table`` is either f32 channel-last rows (packed to
     bf16 here) or the bf16 row table a previous layer produced.  Shapes the tensor-core kernel does not
     cover run on the fp32 kernel (with an fp32 image built on demand)."""
@@ -246,14 +305,36 @@ def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, w
         if rows is not table:
             ld = rows.shape[2]
         return sa_forward_f32(alt, xyz, new_xyz, idx, rows, ld, c, use_xyz, inv_radius, want_rows)
+    c1 = dims[1]
+    image, c_eff = img.image, c
+    if split_first_layer(c, c1) and lib.pn2_sa_tc_supported(c1, c1, dims[2], dims[3], npoint, nsample):
+        # per-point half of layer 1 first (csrc/lin_tc.cu); the fused kernel then gathers c1-wide rows
+        pair = None
+        if table.dtype != torch.bfloat16:
+            # f32 rows read in place: raw_skip elements precede feature 0 in each ld-pitched, 16-byte aligned row
+            kin = _rup(raw_skip + c, 4)
+            base = table.data_ptr() - 4 * raw_skip
+            if ld % 4 == 0 and kin <= ld and base % 16 == 0 and table.stride() == (N * ld, ld, 1):
+                pair = img.split(kin, raw_skip, False)
+                if pair is not None:
+                    table = lin_rows(pair[0], table, ctypes.c_void_p(base), B * N, kin, c1, False, ld).view(B, N, c1)
+        if pair is None:
+            if table.dtype != torch.bfloat16:
+                table = bf16_rows(table, ld, c)
+            kin = table.shape[2]
+            pair = img.split(kin, 0, True)
+            if pair is not None:
+                table = lin_rows(pair[0], table, ptr(table), B * N, kin, c1, True, kin).view(B, N, c1)
+        if pair is not None:
+            image, c_eff = pair[1], c1
     if table.dtype != torch.bfloat16:
         table = bf16_rows(table, ld, c)
     cout = dims[3]
     out = torch.empty((B, cout, npoint), dtype=torch.float32, device=xyz.device)
     out_rows = torch.empty((B, npoint, cout), dtype=torch.bfloat16, device=xyz.device) if want_rows else None
     with torch.cuda.device(xyz.device):
-        check(lib.pn2_sa_tc_forward(B, N, npoint, nsample, c, dims[1], dims[2], dims[3], float(inv_radius), ptr(xyz),
-                                    ptr(new_xyz), ptr(table), ptr(idx), ptr(img.image), ptr(out), ptr(out_rows),
+        check(lib.pn2_sa_tc_forward(B, N, npoint, nsample, c_eff, dims[1], dims[2], dims[3], float(inv_radius), ptr(xyz),
+                                    ptr(new_xyz), ptr(table), ptr(idx), ptr(image), ptr(out), ptr(out_rows),
                                     stream_ptr()), "sa_tc_forward")
     return out, out_rows
 

@@ -38,7 +38,13 @@ def _sa_bf16_emulation(xyz, feats, folded, npoint, radius, nsample):
     gf = orc.group_points(_bf16(feats).contiguous(), idx)
     (w1, b1), (w2, b2), (w3, b3) = folded
     b1q = _bf16(b1) + _bf16(b1 - _bf16(b1))
-    x = torch.einsum("oc,bcps->bops", _bf16(w1[:, :3]), gx) + torch.einsum("oc,bcps->bops", _bf16(w1[:, 3:]), gf)
+    from situation3d_b200.fused import split_first_layer
+    if split_first_layer(feats.shape[1], w1.shape[0]):
+        # split first layer (csrc/lin_tc.cu): the feature half is computed per point and rounded to bf16
+        pp = _bf16(torch.einsum("oc,bcn->bon", _bf16(w1[:, 3:]), _bf16(feats)))
+        x = torch.einsum("oc,bcps->bops", _bf16(w1[:, :3]), gx) + orc.group_points(pp.contiguous(), idx)
+    else:
+        x = torch.einsum("oc,bcps->bops", _bf16(w1[:, :3]), gx) + torch.einsum("oc,bcps->bops", _bf16(w1[:, 3:]), gf)
     x = _bf16(torch.relu(x + b1q[None, :, None, None]))
     x = _bf16(torch.relu(torch.einsum("oc,bcps->bops", _bf16(w2), x) + b2[None, :, None, None]))
     x = torch.relu(torch.einsum("oc,bcps->bops", _bf16(w3), x) + b3[None, :, None, None])
@@ -127,3 +133,32 @@ def test_fp_tc_vs_bf16_emulation(n, m, ck, cs, mlp):
     scale = float(want.abs().max())
     assert float((out.cpu() - want).abs().max()) <= 6e-3 * scale
     torch.testing.assert_close(out_rows.float().cpu().transpose(1, 2), out.cpu(), rtol=1e-2, atol=1e-2 * scale)
+
+
+@pytest.mark.parametrize("rows,c,skip,ld,c1,bf16_in", [
+    (1000, 129, 3, 132, 64, False),      # SA1: point_clouds rows read in place
+    (300, 61, 0, 64, 128, False),
+    (128 * 5, 256, 0, 256, 128, True),   # SA3 / SA4: bf16 rows of the previous layer
+    (77, 129, 0, 136, 64, True),
+])
+def test_lin_tc_row_gemm(rows, c, skip, ld, c1, bf16_in):
+    """P = X W^T of the split first layer against the same product in PyTorch (bf16 operands, fp32 sum)."""
+    from situation3d_b200 import fused
+    from situation3d_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(rows + c)
+    w = torch.randn(c1, 3 + c, generator=g).cuda()
+    x = torch.randn(rows, ld, generator=g)
+    if bf16_in:
+        x[:, c:] = 0                       # padding columns of a bf16 row table are zero
+        xd = x.bfloat16().cuda()
+        kin = ld
+    else:
+        xd = x.cuda()
+        kin = (skip + c + 3) // 4 * 4
+    assert lib.pn2_lin_tc_supported(kin, c1, int(bf16_in))
+    image = torch.empty(lib.pn2_lin_tc_weight_image_bytes(kin, c1), dtype=torch.uint8, device="cuda")
+    check(lib.pn2_lin_tc_pack_weights(kin, skip, c, c1, ptr(w), 3 + c, 3, ptr(image), stream_ptr()), "pack")
+    got = fused.lin_rows(image, xd, ptr(xd), rows, kin, c1, bf16_in, ld).float().cpu()
+    want = (_bf16(x[:, skip:skip + c]) @ _bf16(w[:, 3:].cpu()).t())
+    err = (got - want).abs()
+    assert float((err - 2 ** -8 * want.abs()).max()) <= 1e-3      # one bf16 rounding of the result
