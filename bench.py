@@ -172,13 +172,15 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
     imgs = net._fused_images(pc)
     xyz = pc[..., :3].contiguous()
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=pc.device)
+    flush = torch.empty(1024 * 1024 * 1024 // 4, dtype=torch.float32, device=pc.device)
 
     def timeit(fn):
         fn()
         ts = []
         for _ in range(reps):
-            flush.zero_()                       # 256 MB write: evicts L2 between repetitions
+            # 1 GB write: evicts L2 between repetitions and keeps the GPU busy (~170 us) while the host
+            # enqueues the launch, so the events bracket device time, not launch latency
+            flush.zero_()
             s, e = ev(), ev()
             s.record()
             fn()
@@ -188,50 +190,71 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
         return statistics.median(ts) * 1e-3
 
     rows = []
-    src_xyz, table, ld, c = xyz, pc[..., 3:], W, C
-    elt = 4 if precision == "fp32" else 2
+    src_xyz, table, ld, c, skip = xyz, pc[..., 3:], W, C, 3
     feats_rows = []
     cxyz_all = []
     for lvl, m in enumerate(sas):
         n_in = src_xyz.shape[1]
+        name = "sa%d" % (lvl + 1)
         inds, cxyz = fused.fps_with_xyz(src_xyz, m.npoint)
         t = timeit(lambda: fused.fps_with_xyz(src_xyz, m.npoint))
-        rows.append({"kernel": "fps_sa%d" % (lvl + 1), "bound": "hbm", "seconds": t,
-                     "alg_bytes": B * (12 * n_in + 16 * m.npoint), "rounds_per_s": B * (m.npoint - 1) / t / B})
+        rows.append({"kernel": "fps_" + name, "bound": "hbm", "seconds": t,
+                     "alg_bytes": B * (12 * n_in + 16 * m.npoint), "rounds_per_s": (m.npoint - 1) / t})
         idx = fused.ball_query(src_xyz, cxyz, m.radius, m.nsample)
         t = timeit(lambda: fused.ball_query(src_xyz, cxyz, m.radius, m.nsample))
-        rows.append({"kernel": "ball_query_sa%d" % (lvl + 1), "bound": "hbm", "seconds": t,
+        rows.append({"kernel": "ball_query_" + name, "bound": "hbm", "seconds": t,
                      "alg_bytes": B * (12 * (n_in + m.npoint) + 4 * m.npoint * m.nsample)})
         inv_r = 1.0 / m.radius
-        run = lambda: fused.SA_FORWARD[precision](imgs[lvl], src_xyz, cxyz, idx, table, ld, c, True, inv_r,
-                                                  raw_skip=3 if lvl == 0 else 0)
-        out, out_rows = run()
-        t = timeit(run)
         dims = imgs[lvl].dims
-        flops = 2 * B * m.npoint * m.nsample * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        pairs = B * m.npoint * m.nsample
+        flops = 2 * pairs * sum(a * b for a, b in zip(dims[:-1], dims[1:]))          # the reference's 1x1 convs
         wbytes = 4 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
         abytes = B * (4 * (c + 3) * min(n_in, m.npoint * m.nsample) + 4 * m.npoint * m.nsample
                       + 2 * 4 * dims[-1] * m.npoint) + wbytes
-        rows.append({"kernel": "sa%d_fused_%s" % (lvl + 1, precision), "bound": "tensor", "seconds": t,
-                     "alg_flops": flops, "alg_bytes": abytes})
+        if precision == "bf16" and not imgs[lvl].f32_only:
+            # the tensor-core arm is two launches: the row table (bf16 pack, or the per-point half of layer 1)
+            # and the fused gather + MLP + max-pool kernel
+            prep = lambda: fused.sa_bf16_table(imgs[lvl], table, ld, c, B, n_in, m.npoint, m.nsample, skip)
+            tab, image, c_eff = prep()
+            split = c_eff != c
+            t_prep = timeit(prep) if (split or table.dtype != torch.bfloat16) else 0.0
+            out = torch.empty((B, dims[3], m.npoint), dtype=torch.float32, device=pc.device)
+            out_rows = torch.empty((B, m.npoint, dims[3]), dtype=torch.bfloat16, device=pc.device)
+            run = lambda: fused.sa_bf16_fused(dims, image, c_eff, src_xyz, cxyz, idx, tab, inv_r, True, out, out_rows)
+            run()
+            t = timeit(run)
+            lin_flops = 2 * pairs * c * dims[1] if split else 0      # reference FLOPs the per-point GEMM stands for
+            if t_prep > 0:
+                in_bytes = B * n_in * (ld * 4 if table.dtype != torch.bfloat16 else tab.shape[2] * 2)
+                rows.append({"kernel": "%s_%s" % (name, "pointwise_l1" if split else "pack_rows"), "bound": "hbm",
+                             "seconds": t_prep, "alg_bytes": in_bytes + tab.numel() * 2})
+            rows.append({"kernel": "%s_fused_bf16" % name, "bound": "tensor", "seconds": t,
+                         "alg_flops": flops - lin_flops, "alg_bytes": abytes,
+                         "layer_tflops": flops / (t + t_prep) / 1e12})
+        else:
+            run = lambda: fused.SA_FORWARD[precision](imgs[lvl], src_xyz, cxyz, idx, table, ld, c, True, inv_r, raw_skip=skip)
+            out, out_rows = run()
+            t = timeit(run)
+            rows.append({"kernel": "%s_fused_%s" % (name, precision), "bound": "tensor", "seconds": t,
+                         "alg_flops": flops, "alg_bytes": abytes})
         feats_rows.append(out_rows)
         cxyz_all.append(cxyz)
-        src_xyz, table, ld, c = cxyz, out_rows, out_rows.shape[2], out_rows.shape[2]
+        src_xyz, table, ld, c, skip = cxyz, out_rows, out_rows.shape[2], out_rows.shape[2], 0
     known_rows = feats_rows[3]
-    for name, (u, k), skip in (("fp1", (2, 3), feats_rows[2]), ("fp2", (1, 2), feats_rows[1])):
+    for name, (u, k), skip_rows in (("fp1", (2, 3), feats_rows[2]), ("fp2", (1, 2), feats_rows[1])):
         un, kn = cxyz_all[u], cxyz_all[k]
         d2, i3 = fused.three_nn(un, kn)
         t = timeit(lambda: fused.three_nn(un, kn))
         rows.append({"kernel": "three_nn_" + name, "bound": "hbm", "seconds": t,
                      "alg_bytes": B * (12 * (un.shape[1] + kn.shape[1]) + 24 * un.shape[1])})
         img = imgs[4 if name == "fp1" else 5]
-        run = lambda: fused.FP_FORWARD[precision](img, d2, i3, known_rows, skip)
+        run = lambda: fused.FP_FORWARD[precision](img, d2, i3, known_rows, skip_rows)
         _, out_rows = run()
         t = timeit(run)
         dims = img.dims
         n = un.shape[1]
         flops = 2 * B * n * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
-        abytes = B * (4 * known_rows.shape[2] * kn.shape[1] + 4 * skip.shape[2] * n + 24 * n + 2 * 4 * dims[-1] * n) \
+        abytes = B * (4 * known_rows.shape[2] * kn.shape[1] + 4 * skip_rows.shape[2] * n + 24 * n + 2 * 4 * dims[-1] * n) \
             + 4 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
         rows.append({"kernel": "%s_fused_%s" % (name, precision), "bound": "tensor", "seconds": t,
                      "alg_flops": flops, "alg_bytes": abytes})
@@ -247,6 +270,15 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
         r["frac"] = r["achieved"] / r["peak"]
         r["us"] = r.pop("seconds") * 1e6
     return rows
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the bench kernels from the committed ncu --set full captures
+    (profiles/ncu_traffic.json: kernel -> dram__bytes_read.sum + dram__bytes_write.sum)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
 
 
 def reference_cuda_arm(pc, sd, steps=3):
@@ -345,11 +377,14 @@ def run_ours(args, rank, local_rank, world):
         for ln in lanes:
             base.wait_stream(ln)
         barrier()
+        from situation3d_b200._lib import lib as _pn2
+        launches0 = _pn2.pn2_launch_count()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(base)
         for ln in lanes:
             ln.wait_event(s)
         run_steps(K)
+        launches = int(_pn2.pn2_launch_count() - launches0)      # this library's kernels, counted at the launch sites
         for ln in lanes:
             base.wait_stream(ln)
         e.record(base)
@@ -421,7 +456,6 @@ def run_ours(args, rank, local_rank, world):
         barrier()
 
     if rank == 0:
-        launches_per_step = 4 + 4 + 4 + 2 + 2          # fps, ball query, fused SA, three_nn, fused FP
         line = {"metric": METRIC, "value": world * B * K / dt, "unit": UNIT, "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
@@ -434,19 +468,25 @@ def run_ours(args, rank, local_rank, world):
                 "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "ms_per_step": 1e3 * dt_e2e / K,
                         "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                         "api": "Pointnet2Backbone.forward(data_dict) on pinned host point_clouds"},
-                "gpu_launches": launches_per_step * K, "clocks": clocks, "peaks": pk}
+                "gpu_launches": launches * world, "gpu_launches_per_step": launches / K, "clocks": clocks, "peaks": pk}
         if rows:
             dom = max(rows, key=lambda r: r["share"])
+            traffic = ncu_traffic()
             line["roofline"] = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
-                                "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
+                                "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
+                                "traffic": traffic.get(dom["kernel"]),
                                 "share_of_step": dom["share"], "us_per_launch": dom["us"],
                                 "peak_source": pk["source"] + (" burst" if dom["bound"] == "tensor" else "")}
             if "rounds_per_s" in dom:
                 line["roofline"]["rounds_per_s"] = dom["rounds_per_s"]
             line["roofline_kernels"] = [
                 {k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()
-                 if k in ("kernel", "bound", "us", "share", "achieved", "unit", "frac", "hbm_gbs", "rounds_per_s")}
+                 if k in ("kernel", "bound", "us", "share", "achieved", "unit", "frac", "hbm_gbs", "rounds_per_s",
+                          "layer_tflops")}
                 for r in rows]
+            for r in line["roofline_kernels"]:
+                if r["kernel"] in traffic:
+                    r["traffic"] = traffic[r["kernel"]]
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         if ref_cuda:

@@ -62,7 +62,9 @@ typedef void *pn2_stream_t;
 int pn2_version(void);                       /* major*10000 + minor*100 + patch */
 const char *pn2_error_string(int code);
 const char *pn2_last_cuda_error(void);       /* text of the last CUDA failure on this thread */
-int pn2_device_check(void);                  /* PN2_OK iff the current device is compute capability 10.x */
+int pn2_device_check(void);
+/* kernels launched by this library since it was loaded (every entry point counts its own launches) */
+unsigned long long pn2_launch_count(void);                  /* PN2_OK iff the current device is compute capability 10.x */
 
 /* ---- the nine reference operators ------------------------------------- */
 

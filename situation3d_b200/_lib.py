@@ -37,6 +37,7 @@ _PROTOTYPES = {
     "pn2_error_string": (c_char_p, [_i]),
     "pn2_last_cuda_error": (c_char_p, []),
     "pn2_device_check": (_i, []),
+    "pn2_launch_count": (ctypes.c_ulonglong, []),
     "pn2_gather_points": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "pn2_gather_points_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "pn2_furthest_point_sampling_workspace_bytes": (c_size_t, [_i, _i, _i]),

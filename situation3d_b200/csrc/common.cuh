@@ -16,6 +16,7 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; persistent grids are si
 
 // ---- error plumbing -------------------------------------------------------
 void set_cuda_error(cudaError_t e, const char *where);
+void count_launches(int n);   // pn2_launch_count(): kernels this library has launched (bench.py's gpu_launches)
 
 #define PN2_CUDA_TRY(expr)                                   \
     do {                                                     \
@@ -28,6 +29,7 @@ void set_cuda_error(cudaError_t e, const char *where);
 
 #define PN2_LAUNCH_CHECK(name)                               \
     do {                                                     \
+        ::pn2::count_launches(1);                            \
         cudaError_t _e = cudaGetLastError();                 \
         if (_e != cudaSuccess) {                             \
             ::pn2::set_cuda_error(_e, name);                 \

@@ -427,6 +427,7 @@ static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     PN2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, n, m, pl.lg_bs, pl.cnt, xyz, idxs, new_xyz, prof));
+    count_launches(1);
     return PN2_OK;
 }
 

@@ -429,6 +429,7 @@ extern "C" int pn2_ball_query_ws(int b, int n, int m, float radius, int nsample,
     dim3 qgrid(ceil_div(m, warps), b);
     bq_grid_query_kernel<<<qgrid, warps * 32, per_warp * warps, s>>>(n, m, radius * radius, nsample, wpl, warps, new_xyz,
                                                                     params, start, sorted, idx);
+    count_launches(4);   // setup, bin x2, scan (the query kernel is counted by the check below)
     PN2_LAUNCH_CHECK("ball_query_grid");
     return PN2_OK;
 }

@@ -286,29 +286,13 @@ def _f32_rows(rows):
     return rows if rows is None or rows.dtype == torch.float32 else rows.float()
 
 
-def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True, raw_skip=0):
-    """Fused SA layer on tcgen05 (pn2_sa_tc_forward).  ``table`` is either f32 channel-last rows (packed to
-    bf16 here) or the bf16 row table a previous layer produced.  Shapes the tensor-core kernel does not
-    cover run on the fp32 kernel (with an fp32 image built on demand)."""
-    B, N, _ = xyz.shape
-    npoint, nsample = idx.shape[1], idx.shape[2]
+def sa_bf16_table(img, table, ld, c, B, N, npoint, nsample, raw_skip=0):
+    """What the tensor-core SA kernel gathers from, and the weight image that goes with it: the c1-wide
+    per-point layer-1 rows (split first layer, csrc/lin_tc.cu) when that is the cheaper gather, else the bf16
+    feature rows.  Returns (table (B,N,row_elems) bf16, weight image, channels per row)."""
     dims = img.dims
-    ok = use_xyz and not img.f32_only and len(dims) == 4 and \
-        lib.pn2_sa_tc_supported(c, dims[1], dims[2], dims[3], npoint, nsample)
-    if not ok:
-        alt = img if img.f32_only else img._f32_alt
-        if alt is None:
-            alt = MlpImage()
-            alt.dims, alt.folded, alt.image = img.dims, img.folded, _pack_f32(img.dims, img.folded)
-            img._f32_alt = alt
-        rows = _f32_rows(table)
-        if rows is not table:
-            ld = rows.shape[2]
-        return sa_forward_f32(alt, xyz, new_xyz, idx, rows, ld, c, use_xyz, inv_radius, want_rows)
     c1 = dims[1]
-    image, c_eff = img.image, c
     if split_first_layer(c, c1) and lib.pn2_sa_tc_supported(c1, c1, dims[2], dims[3], npoint, nsample):
-        # per-point half of layer 1 first (csrc/lin_tc.cu); the fused kernel then gathers c1-wide rows
         pair = None
         if table.dtype != torch.bfloat16:
             # f32 rows read in place: raw_skip elements precede feature 0 in each ld-pitched, 16-byte aligned row
@@ -326,17 +310,49 @@ def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, w
             if pair is not None:
                 table = lin_rows(pair[0], table, ptr(table), B * N, kin, c1, True, kin).view(B, N, c1)
         if pair is not None:
-            image, c_eff = pair[1], c1
+            return table, pair[1], c1
     if table.dtype != torch.bfloat16:
         table = bf16_rows(table, ld, c)
+    return table, img.image, c
+
+
+def sa_bf16_fused(dims, image, c_eff, xyz, new_xyz, idx, table, inv_radius, want_rows=True, out=None, out_rows=None):
+    """pn2_sa_tc_forward over a prepared row table (sa_bf16_table)."""
+    B, N, _ = xyz.shape
+    npoint, nsample = idx.shape[1], idx.shape[2]
     cout = dims[3]
-    out = torch.empty((B, cout, npoint), dtype=torch.float32, device=xyz.device)
-    out_rows = torch.empty((B, npoint, cout), dtype=torch.bfloat16, device=xyz.device) if want_rows else None
+    if out is None:
+        out = torch.empty((B, cout, npoint), dtype=torch.float32, device=xyz.device)
+    if out_rows is None and want_rows:
+        out_rows = torch.empty((B, npoint, cout), dtype=torch.bfloat16, device=xyz.device)
     with torch.cuda.device(xyz.device):
         check(lib.pn2_sa_tc_forward(B, N, npoint, nsample, c_eff, dims[1], dims[2], dims[3], float(inv_radius), ptr(xyz),
                                     ptr(new_xyz), ptr(table), ptr(idx), ptr(image), ptr(out), ptr(out_rows),
                                     stream_ptr()), "sa_tc_forward")
     return out, out_rows
+
+
+def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True, raw_skip=0):
+    """Fused SA layer on tcgen05 (pn2_sa_tc_forward).  ``table`` is either f32 channel-last rows (read in place by
+    the per-point GEMM, or packed to bf16 here) or the bf16 row table a previous layer produced.  Shapes the
+    tensor-core kernel does not cover run on the fp32 kernel (with an fp32 image built on demand)."""
+    B, N, _ = xyz.shape
+    npoint, nsample = idx.shape[1], idx.shape[2]
+    dims = img.dims
+    ok = use_xyz and not img.f32_only and len(dims) == 4 and \
+        lib.pn2_sa_tc_supported(c, dims[1], dims[2], dims[3], npoint, nsample)
+    if not ok:
+        alt = img if img.f32_only else img._f32_alt
+        if alt is None:
+            alt = MlpImage()
+            alt.dims, alt.folded, alt.image = img.dims, img.folded, _pack_f32(img.dims, img.folded)
+            img._f32_alt = alt
+        rows = _f32_rows(table)
+        if rows is not table:
+            ld = rows.shape[2]
+        return sa_forward_f32(alt, xyz, new_xyz, idx, rows, ld, c, use_xyz, inv_radius, want_rows)
+    table, image, c_eff = sa_bf16_table(img, table, ld, c, B, N, npoint, nsample, raw_skip)
+    return sa_bf16_fused(dims, image, c_eff, xyz, new_xyz, idx, table, inv_radius, want_rows)
 
 
 def _bf16_rows(rows):
