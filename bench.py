@@ -47,8 +47,10 @@ def parse():
     ap.add_argument("--precision", default=None, help="fp32 | bf16 (default: bf16 when built, else fp32)")
     ap.add_argument("--batch", type=int, default=8, help="scenes per GPU per step")
     ap.add_argument("--points", type=int, default=40000)
-    ap.add_argument("--lanes", type=int, default=6,
+    ap.add_argument("--lanes", type=int, default=8,
                     help="batches in flight per GPU: step i runs on CUDA stream i %% lanes (1 = strictly serial steps)")
+    ap.add_argument("--fps-sms", type=int, default=0,
+                    help="give the sampling chains their own group of >= this many SMs (CUDA green contexts); 0 = off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
@@ -357,7 +359,13 @@ def run_ours(args, rank, local_rank, world):
         # K steps, `lanes` of them in flight: the sampling chain of a batch is a serial, latency-bound
         # kernel on 128 SMs; batches on other streams fill the machine meanwhile
         base = torch.cuda.current_stream(dev)
-        lanes = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.lanes))]
+        part = None
+        if args.fps_sms > 0:
+            from situation3d_b200.streams import SmPartition
+            part = SmPartition(args.fps_sms, dev)
+            net.sm_partition = part
+            net._side_streams.clear()
+        lanes = [part.stream(part.MAIN) if part else torch.cuda.Stream(device=dev) for _ in range(max(1, args.lanes))]
         outs = [None] * len(lanes)
 
         def run_steps(steps):
@@ -464,6 +472,7 @@ def run_ours(args, rank, local_rank, world):
                            "scenes_per_gpu": B, "points": args.points, "feature_channels": 129,
                            "precision": precision, "sharding": "by scene, no collective",
                            "batches_in_flight": len(lanes),
+                           "sm_partition": {"fps": part.sms[0], "main": part.sms[1]} if part else None,
                            "l2": "each input batch is %.0f MB (> 126 MB L2); two batches alternate" % (in_bytes / 1e6)},
                 "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "ms_per_step": 1e3 * dt_e2e / K,
                         "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,

@@ -222,6 +222,17 @@ int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, int c1, int 
                       const int *idx, const void *known_rows, const void *skip_rows,
                       const void *weight_image, float *out, void *out_rows, pn2_stream_t stream);
 
+/* ---- SM partitions for callers that keep several batches in flight (csrc/sm_partition.cu) ----------
+ * The sampling chain of a batch is a latency-bound kernel of half-SM CTAs that lives ~2 ms; the fused MLP
+ * kernels are persistent whole-SM CTAs.  pn2_sm_partition_create splits the current device's SMs into a first
+ * group of at least sms_first SMs and the rest (CUDA green contexts); streams created on a group confine their
+ * kernels to it, and the persistent kernels of this library size their grids from the stream's group
+ * (pn2_stream_sm_count).  Purely a scheduling aid: results do not depend on it. */
+int pn2_sm_partition_create(int sms_first, void **handle);
+int pn2_sm_partition_sms(void *handle, int which);
+int pn2_sm_partition_stream_create(void *handle, int which, void **stream);
+int pn2_stream_sm_count(pn2_stream_t stream);
+
 /* Diagnostic: while prof (device, 32 x int64) is non-NULL, the pn2_sa_tc_forward kernels record the SM cycles
  * CTA 0 spends per phase.  Software-pipelined kernel: [0..5] epilogue warp 0 (wait D1, E1, wait D2, E2, wait D3,
  * E3), [7] tiles, [8..10] layer-1 issuer, [11..14] layer-2/3 issuer, [16..18] gather warps. */

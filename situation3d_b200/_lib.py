@@ -38,6 +38,10 @@ _PROTOTYPES = {
     "pn2_last_cuda_error": (c_char_p, []),
     "pn2_device_check": (_i, []),
     "pn2_launch_count": (ctypes.c_ulonglong, []),
+    "pn2_sm_partition_create": (_i, [_i, POINTER(_p)]),
+    "pn2_sm_partition_sms": (_i, [_p, _i]),
+    "pn2_sm_partition_stream_create": (_i, [_p, _i, POINTER(_p)]),
+    "pn2_stream_sm_count": (_i, [_p]),
     "pn2_gather_points": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "pn2_gather_points_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "pn2_furthest_point_sampling_workspace_bytes": (c_size_t, [_i, _i, _i]),

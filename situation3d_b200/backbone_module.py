@@ -50,6 +50,7 @@ class Pointnet2Backbone(nn.Module):
         self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
         self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
         self._side_streams = {}
+        self.sm_partition = None      # optional streams.SmPartition: sampling side streams come from its FPS group
 
     @staticmethod
     def _break_up_pc(pc):
@@ -82,7 +83,9 @@ class Pointnet2Backbone(nn.Module):
         key = (dev.index, main.cuda_stream)
         side = self._side_streams.get(key)
         if side is None:
-            side = self._side_streams[key] = torch.cuda.Stream(device=dev)
+            part = self.sm_partition
+            side = part.stream(part.FPS) if part is not None else torch.cuda.Stream(device=dev)
+            self._side_streams[key] = side
 
         # buffers are allocated on the main stream; the side stream only fills them
         inds = [torch.empty((B, m.npoint), dtype=torch.int32, device=dev) for m in sas]

@@ -16,7 +16,8 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; persistent grids are si
 
 // ---- error plumbing -------------------------------------------------------
 void set_cuda_error(cudaError_t e, const char *where);
-void count_launches(int n);   // pn2_launch_count(): kernels this library has launched (bench.py's gpu_launches)
+void count_launches(int n);
+int stream_sm_count(cudaStream_t stream);   // sm_partition.cu: SMs of the stream's partition, else of the device   // pn2_launch_count(): kernels this library has launched (bench.py's gpu_launches)
 
 #define PN2_CUDA_TRY(expr)                                   \
     do {                                                     \

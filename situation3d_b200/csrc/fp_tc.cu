@@ -313,9 +313,7 @@ extern "C" int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, i
     p.image = static_cast<const unsigned char *>(weight_image);
     p.out = out;
     p.out_rows = static_cast<__nv_bfloat16 *>(out_rows);
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = stream_sm_count(as_stream(stream));
     PN2_CUDA_TRY(cudaFuncSetAttribute(fp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.s.smem_bytes));
     fp_tc_kernel<<<min(p.ntiles, sms), kFpThreads, p.s.smem_bytes, as_stream(stream)>>>(p);
     PN2_LAUNCH_CHECK("fp_tc_forward");

@@ -251,12 +251,35 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
     if (profiling) tprev = clock64();
 #define PN2_FPS_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
 
+    // The thread's candidate (its largest running distance; earliest slot among equals) is cached across rounds
+    // with its coordinates.  Running distances only shrink, and no earlier slot can equal the cached maximum (it
+    // would have been the candidate), so the candidate can only change when ITS OWN distance shrinks: one scalar
+    // distance per round decides, and the full tournament + coordinate fetch runs only then (every round at the
+    // start, a few per cent of the rounds once the samples are dense).
+    Cand best;
+    float bx, by, bz;
+    auto tournament = [&]() {
+        Cand cd[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) { cd[i].v = pt[i]; cd[i].i = i; }
+#pragma unroll
+        for (int st = 1; st < P; st *= 2)
+#pragma unroll
+            for (int i = 0; i + st < P; i += 2 * st) take_later_if_greater(cd[i], cd[i + st]);
+        best = cd[0];
+        bx = sx[best.i * T + tid]; by = sy[best.i * T + tid]; bz = sz[best.i * T + tid];
+    };
+    tournament();
+
     for (int j = 1; j < m; ++j) {
         const int r = j - 1;
         const uint32_t boff = (uint32_t)(r & 1);
-        // ---- distance update: all slots independently, then a tournament (depth log2 P) ----
+        // ---- distance update: all slots independently ----
         const uint64_t nx2 = pack2(-ox, -ox), ny2 = pack2(-oy, -oy), nz2 = pack2(-oz, -oz);
-        Cand cd[P];
+        // does the new sample shrink the candidate's own distance?  (same recipe as the slots: sqdist3)
+        // (with few slots per thread the tournament is cheaper than the test: always run it)
+        constexpr bool kLazy = P >= 12;
+        const bool stale = !kLazy || fminf(sqdist3(bx, by, bz, ox, oy, oz), best.v) != best.v;
 #pragma unroll
         for (int i = 0; i < P; i += 2) {
             uint64_t x2 = px2[i / 2], y2 = py2[i / 2], z2 = pz2[i / 2];
@@ -272,16 +295,8 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
             unpack2(d, d0, d1);
             pt[i] = fminf(d0, pt[i]);
             pt[i + 1] = fminf(d1, pt[i + 1]);
-            cd[i].v = pt[i]; cd[i].i = i;
-            cd[i + 1].v = pt[i + 1]; cd[i + 1].i = i + 1;
         }
-#pragma unroll
-        for (int st = 1; st < P; st *= 2)
-#pragma unroll
-            for (int i = 0; i + st < P; i += 2 * st) take_later_if_greater(cd[i], cd[i + st]);
-        const Cand best = cd[0];
-        // the candidate's coordinates (3 LDS instead of carrying xyz through the tournament)
-        const float bx = sx[best.i * T + tid], by = sy[best.i * T + tid], bz = sz[best.i * T + tid];
+        if (stale) tournament();
         const uint32_t hi = best.v >= 0.f ? __float_as_uint(best.v) + 1u : 0u;
         PN2_FPS_MARK(0)
 
@@ -306,24 +321,19 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
         }
         PN2_FPS_MARK(2)
         // ---- winner of the whole scene: every warp reduces the same table ----
-        uint4 e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            e[i] = i < K ? lds128(tab + (uint32_t)(i * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
-        int ei[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ei[i] = i;
-#pragma unroll
-        for (int st = 1; st < 8; st *= 2)
-#pragma unroll
-            for (int i = 0; i + st < 8; i += 2 * st)
-                if (e[i + st].x > e[i].x) { e[i] = e[i + st]; ei[i] = ei[i + st]; }
-        const uint32_t smax = __reduce_max_sync(kFull, e[0].x);
-        const int ssrc = __ffs(__ballot_sync(kFull, e[0].x == smax)) - 1;   // lowest lane = lowest slot
-        const float nx = __uint_as_float(__shfl_sync(kFull, e[0].y, ssrc));
-        const float ny = __uint_as_float(__shfl_sync(kFull, e[0].z, ssrc));
-        const float nz = __uint_as_float(__shfl_sync(kFull, e[0].w, ssrc));
-        const int sslot = ssrc * K + __shfl_sync(kFull, ei[0], ssrc);
+        // lane l holds table positions i*32 + l, i < K: keep the largest key, the earliest position among equals
+        uint4 e0 = lds128(tab + (uint32_t)lane * 16);
+        int e0i = 0;
+        for (int i = 1; i < K; ++i) {
+            const uint4 ei = lds128(tab + (uint32_t)(i * 32 + lane) * 16);
+            if (ei.x > e0.x) { e0 = ei; e0i = i; }
+        }
+        const uint32_t smax = __reduce_max_sync(kFull, e0.x);
+        const int ssrc = __ffs(__ballot_sync(kFull, e0.x == smax)) - 1;   // lowest lane = lowest slot
+        const float nx = __uint_as_float(__shfl_sync(kFull, e0.y, ssrc));
+        const float ny = __uint_as_float(__shfl_sync(kFull, e0.z, ssrc));
+        const float nz = __uint_as_float(__shfl_sync(kFull, e0.w, ssrc));
+        const int sslot = ssrc * K + __shfl_sync(kFull, e0i, ssrc);
 
         const bool none = smax == 0u;   // every point skipped: the reference's reduction leaves besti = 0
         ox = none ? p0x : nx; oy = none ? p0y : ny; oz = none ? p0z : nz;

@@ -382,9 +382,7 @@ static uint32_t lin_tma_smem_bytes(int kin, int K, int c1)
 template <int C1>
 static int launch_lin_tma(const LinParams &p, cudaStream_t stream)
 {
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = stream_sm_count(stream);
     const uint32_t smem = lin_tma_smem_bytes(p.kin, p.K, C1);
     auto kern = lin_tc_tma_kernel<C1>;
     PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -401,9 +399,7 @@ static uint32_t lin_smem_bytes(int K, int c1)
 template <int C1, bool BF16_IN>
 static int launch_lin(const LinParams &p, cudaStream_t stream)
 {
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = stream_sm_count(stream);
     const uint32_t smem = lin_smem_bytes(p.K, C1);
     auto kern = lin_tc_kernel<C1, BF16_IN>;
     PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

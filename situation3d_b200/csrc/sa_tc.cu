@@ -1199,9 +1199,7 @@ template <int NS>
 static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
 {
     const SaTcParams &p = p_in;
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = stream_sm_count(stream);
     // warp-specialised two-stage variant when the resident weights and two gather stages fit
     const uint32_t pipe_fixed = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + p.s.bias_bytes + 128u;
     const uint32_t budget = 226u * 1024u;
