@@ -163,7 +163,7 @@ struct SaTcParams {
     int nstage;             // gather ring depth of the warp-specialised kernel (2..4)
     int nregion, nslot;     // pipelined kernel: shared-memory tile regions (<= 8) and TMEM accumulator slots (2 or 4)
     uint32_t blk;
-    int debug;              // diagnostics (PN2_SA_TC_DEBUG): bit 0 skip the feature gather, bit 1 skip the xyz chunk
+    int debug;              // diagnostics (PN2_SA_TC_DEBUG): 1 skip the feature gather, 4 skip E2's proxy fence, 32 gather rows 0..127
     long long *prof;        // diagnostics: per-phase SM cycles of CTA 0 (16 x int64) or NULL
     float inv_radius;
     const float *xyz, *new_xyz;
@@ -684,19 +684,14 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // E1: D1 (fp32, this thread's row) -> ReLU -> bf16 pairs -> TMEM columns of the layer-2 A operand
 template <int C1>
-__device__ __forceinline__ void v3_epi1(uint32_t d_taddr, uint32_t a_taddr, int debug)
+__device__ __forceinline__ void v3_epi1(uint32_t d_taddr, uint32_t a_taddr)
 {
 #pragma unroll
     for (int c0 = 0; c0 < C1; c0 += 64) {
         uint32_t va[32], vb[32];
-        if (debug & 16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0u;
-        } else {
         tmem_ld32_issue(d_taddr + c0, va);
         tmem_ld32_issue(d_taddr + c0 + 32, vb);
         tmem_ld_wait();
-        }
         uint32_t pa[16], pb[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -711,21 +706,16 @@ __device__ __forceinline__ void v3_epi1(uint32_t d_taddr, uint32_t a_taddr, int 
 
 // E2: D2 + bias -> ReLU -> bf16 -> K-major 128B-swizzled rows of the region (the layer-3 B operand)
 template <int C2>
-__device__ __forceinline__ void v3_epi2(uint32_t d_taddr, unsigned char *region, int row, const float *bias2, int debug)
+__device__ __forceinline__ void v3_epi2(uint32_t d_taddr, unsigned char *region, int row, const float *bias2)
 {
     unsigned char *row_base = region + row * 128;
     const uint32_t r7 = (uint32_t)(row & 7);
 #pragma unroll
     for (int c0 = 0; c0 < C2; c0 += 64) {
         uint32_t v[2][32];
-        if (debug & 16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[0][j] = v[1][j] = 0u;
-        } else {
         tmem_ld32_issue(d_taddr + c0, v[0]);
         tmem_ld32_issue(d_taddr + c0 + 32, v[1]);
         tmem_ld_wait();
-        }
         unsigned char *tile_base = row_base + (c0 / 64) * (kTile * 128);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -759,14 +749,9 @@ __device__ __forceinline__ void v3_epi3(const SaTcParams &p, uint32_t d_taddr, i
 #pragma unroll
         for (int q0 = 0; q0 < kTile; q0 += 64) {
             uint32_t v[2][32];
-            if (p.debug & 16) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[0][j] = v[1][j] = 0u;
-            } else {
             tmem_ld32_issue(d_taddr + mt * kTile + q0, v[0]);
             tmem_ld32_issue(d_taddr + mt * kTile + q0 + 32, v[1]);
             tmem_ld_wait();
-            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int col = q0 + h * 32;
@@ -782,10 +767,8 @@ __device__ __forceinline__ void v3_epi3(const SaTcParams &p, uint32_t d_taddr, i
                     if ((col + 32) % NS == 0) {
                         const int cl = col / NS;
                         const float o = fmaxf(run + bias, 0.f);
-                        if (!(p.debug & 8) || o == 12345.f) {
                         out[cl] = o;
                         if (out_t) out_t[(size_t)cl * C3] = __float2bfloat16_rn(o);
-                        }
                         run = -3.0e38f;
                     }
                 } else {
@@ -1045,7 +1028,7 @@ sa_tc_v3_kernel(const SaTcParams p)
             tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 0), (uint32_t)((it / T) & 1));
             tc_fence_after();
             PN2_MARK(0)
-            v3_epi1<C1>(my_tmem + sl * kBlk, my_tmem + sl * kBlk + kAOff, p.debug);
+            v3_epi1<C1>(my_tmem + sl * kBlk, my_tmem + sl * kBlk + kAOff);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(bar_aready + 8u * (sl * 2 + 0));
@@ -1057,7 +1040,7 @@ sa_tc_v3_kernel(const SaTcParams p)
             tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 1), (uint32_t)((it / T) & 1));
             tc_fence_after();
             PN2_MARK(2)
-            v3_epi2<C2>(my_tmem + sl * kBlk, region, row, bias2, p.debug);
+            v3_epi2<C2>(my_tmem + sl * kBlk, region, row, bias2);
             tc_fence_before();
             if (!(p.debug & 4)) fence_proxy_async();
             __syncwarp();
