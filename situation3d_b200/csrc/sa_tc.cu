@@ -877,35 +877,42 @@ sa_tc_v3_kernel(const SaTcParams p)
             const int t_ = blockIdx.x + it_ * gridDim.x, b_ = t_ / p.tiles_per_scene;
             return __ldg(p.idx + (size_t)b_ * p.npoint * NS + (t_ - b_ * p.tiles_per_scene) * kTile + myrow);
         };
-        float px[3] = {0.f, 0.f, 0.f}, cx[3] = {0.f, 0.f, 0.f};
-        auto load_xyz = [&](int it_, int nb_) {
+        // coordinates in flight for tiles it+1 and it+2 (slot = tile parity), indices for it+2 and it+3
+        float px[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, cx[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        auto load_xyz = [&](int it_, int nb_, float (&pv)[3], float (&cv)[3]) {
             if (it_ >= nt) return;
             const int t_ = blockIdx.x + it_ * gridDim.x, b_ = t_ / p.tiles_per_scene;
             const int r0_ = (t_ - b_ * p.tiles_per_scene) * kTile;
             const float *pp = p.xyz + ((size_t)b_ * p.n + nb_) * 3;
             const float *cc = p.new_xyz + ((size_t)b_ * p.npoint + (r0_ + myrow) / NS) * 3;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { px[a] = __ldg(pp + a); cx[a] = __ldg(cc + a); }
+            for (int a = 0; a < 3; ++a) { pv[a] = __ldg(pp + a); cv[a] = __ldg(cc + a); }
         };
-        int nb_cur = load_idx(0), nb_next = load_idx(1);
-        if (p.debug & 32) nb_cur = myrow;
-        load_xyz(0, nb_cur);
-        for (int it = 0; it < nt; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int rg = it % R, u = it / R;
-            const int nb = nb_cur;
+        const bool fixed_rows = (p.debug & 32) != 0;
+        int nb0 = fixed_rows ? myrow : load_idx(0), nb1 = fixed_rows ? myrow : load_idx(1);   // tiles it, it+1
+        int nb2 = fixed_rows ? myrow : load_idx(2);                                           // tile it+2
+        load_xyz(0, nb0, px[0], cx[0]);
+        load_xyz(1, nb1, px[1], cx[1]);
+        for (int it = 0; it < nt; it += 2) {
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            const int itt = it + par;
+            if (itt >= nt) break;
+            const int tile = blockIdx.x + itt * gridDim.x;
+            const int rg = itt % R, u = itt / R;
+            const int nb = nb0;
             const int bi = tile / p.tiles_per_scene;
-            // recentred, normalised xyz of this lane's row, from the coordinates loaded during the previous tile
+            // recentred, normalised xyz of this lane's row, from the coordinates loaded two tiles ago
             float h[3], l[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const float d = __fmul_rn(__fsub_rn(px[a], cx[a]), p.inv_radius);
+                const float d = __fmul_rn(__fsub_rn(px[par][a], cx[par][a]), p.inv_radius);
                 h[a] = __bfloat162float(__float2bfloat16_rn(d));
                 l[a] = d - h[a];
             }
-            nb_cur = (p.debug & 32) ? myrow : nb_next;
-            load_xyz(it + 1, nb_cur);
-            nb_next = load_idx(it + 2);
+            nb0 = nb1; nb1 = nb2;
+            load_xyz(itt + 2, nb1, px[par], cx[par]);
+            nb2 = fixed_rows ? myrow : load_idx(itt + 3);
             if (u > 0) tc_mbar_wait(bar_empty + 8u * rg, (u - 1) & 1);
             PN2_MARK(0)
             unsigned char *region = ring + (size_t)rg * s.region_bytes;
@@ -926,15 +933,16 @@ sa_tc_v3_kernel(const SaTcParams p)
             for (int ch = NCHUNK + 1; ch < K0 / 8; ++ch)
                 *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, K0, myrow, ch)) = make_uint4(0u, 0u, 0u, 0u);
             // the tile issued kLag iterations ago has landed by now: publish it (one arrival per warp)
-            if (it >= lag) {
+            if (itt >= lag) {
                 if (lag == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
                 else if (lag == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
                 else asm volatile("cp.async.wait_group 0;" ::: "memory");
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) tc_mbar_arrive(bar_full + 8u * ((it - lag) % R));
+                if (lane == 0) tc_mbar_arrive(bar_full + 8u * ((itt - lag) % R));
             }
             PN2_MARK(2)
+          }
         }
         // drain: the last `lag` tiles
         cp_async_wait_all();
