@@ -51,6 +51,8 @@ def parse():
                     help="batches in flight per GPU: step i runs on CUDA stream i %% lanes (1 = strictly serial steps)")
     ap.add_argument("--fps-sms", type=int, default=0,
                     help="give the sampling chains their own group of >= this many SMs (CUDA green contexts); 0 = off")
+    ap.add_argument("--no-graphs", action="store_true",
+                    help="enqueue every step from Python instead of replaying a captured CUDA graph per lane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
@@ -368,10 +370,21 @@ def run_ours(args, rank, local_rank, world):
         lanes = [part.stream(part.MAIN) if part else torch.cuda.Stream(device=dev) for _ in range(max(1, args.lanes))]
         outs = [None] * len(lanes)
 
+        graphs = None
+        if not args.no_graphs:
+            # one captured step per lane (situation3d_b200.graphs): replaying it costs the host one cudaGraphLaunch
+            # instead of ~0.8 ms of Python launches, which is what bounds the eager loop once lanes overlap
+            from situation3d_b200.graphs import GraphedBackbone
+            graphs = [GraphedBackbone(net, pool[i % 2], stream=ln, static_input=pool[i % 2]) for i, ln in enumerate(lanes)]
+
         def run_steps(steps):
             for i in range(steps):
-                with torch.cuda.stream(lanes[i % len(lanes)]):
-                    outs[i % len(lanes)] = net({"point_clouds": pool[i % 2]})
+                ln = i % len(lanes)
+                if graphs:
+                    outs[ln] = graphs[ln]()
+                else:
+                    with torch.cuda.stream(lanes[ln]):
+                        outs[ln] = net({"point_clouds": pool[i % 2]})
 
         for ln in lanes:
             ln.wait_stream(base)
@@ -391,8 +404,12 @@ def run_ours(args, rank, local_rank, world):
         s.record(base)
         for ln in lanes:
             ln.wait_event(s)
+        t_host0 = time.perf_counter()
         run_steps(K)
+        host_ms_per_step = 1e3 * (time.perf_counter() - t_host0) / K     # host time to ENQUEUE a step (no sync inside)
         launches = int(_pn2.pn2_launch_count() - launches0)      # this library's kernels, counted at the launch sites
+        if graphs:
+            launches = K * graphs[0].launches_per_replay           # (counted at capture; a replay launches the same kernels)
         for ln in lanes:
             base.wait_stream(ln)
         e.record(base)
@@ -404,7 +421,11 @@ def run_ours(args, rank, local_rank, world):
         # ---- end to end: pinned host input -> H2D -> forward -> D2H of the result, double-buffered ----
         # each lane owns a device input buffer and pinned result buffers; its H2D copy, forward and D2H
         # copies are enqueued on the lane's stream, so lanes overlap each other's copies and kernels
-        dbuf = [torch.empty_like(pool[0]) for _ in lanes]
+        dbuf = [pool[0].clone() for _ in lanes]
+        e2e_graphs = None
+        if not args.no_graphs and not args.no_e2e:
+            graphs = None                                     # release the resident-run graphs' pools
+            e2e_graphs = [GraphedBackbone(net, pool[0], stream=ln, static_input=dbuf[i]) for i, ln in enumerate(lanes)]
         res_host = [{k: torch.empty_like(out[k], device="cpu").pin_memory() for k in ("fp2_features", "fp2_xyz", "fp2_inds")}
                     for _ in lanes]
         out_bytes = sum(v.numel() * v.element_size() for v in res_host[0].values())
@@ -414,7 +435,7 @@ def run_ours(args, rank, local_rank, world):
                 ln = i % len(lanes)
                 with torch.cuda.stream(lanes[ln]):
                     dbuf[ln].copy_(host_pool[i % 2], non_blocking=True)
-                    o = net({"point_clouds": dbuf[ln]})
+                    o = e2e_graphs[ln]() if e2e_graphs else net({"point_clouds": dbuf[ln]})
                     for k, v in res_host[ln].items():
                         v.copy_(o[k], non_blocking=True)
                     outs[ln] = o
@@ -471,13 +492,14 @@ def run_ours(args, rank, local_rank, world):
                                        "xyz+height+128-d multiview (BASELINE configs[1])" % (B, args.points),
                            "scenes_per_gpu": B, "points": args.points, "feature_channels": 129,
                            "precision": precision, "sharding": "by scene, no collective",
-                           "batches_in_flight": len(lanes),
+                           "batches_in_flight": len(lanes), "cuda_graphs": not args.no_graphs,
                            "sm_partition": {"fps": part.sms[0], "main": part.sms[1]} if part else None,
                            "l2": "each input batch is %.0f MB (> 126 MB L2); two batches alternate" % (in_bytes / 1e6)},
                 "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "ms_per_step": 1e3 * dt_e2e / K,
                         "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                         "api": "Pointnet2Backbone.forward(data_dict) on pinned host point_clouds"},
-                "gpu_launches": launches * world, "gpu_launches_per_step": launches / K, "clocks": clocks, "peaks": pk}
+                "gpu_launches": launches * world, "gpu_launches_per_step": launches / K,
+                "host_enqueue_ms_per_step": host_ms_per_step, "clocks": clocks, "peaks": pk}
         if rows:
             dom = max(rows, key=lambda r: r["share"])
             traffic = ncu_traffic()

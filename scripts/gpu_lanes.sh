@@ -1,15 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_fused_gpu.py -m gpu -q --timeout 200 -x -k "graphed or partition" 2>&1 | tail -4
 run() {
-  timeout 300 python bench.py --steps 48 --warmup 3 --lanes $1 --fps-sms $2 --no-cpu-baseline $3 --no-reference-cuda > gpurun_out/bench_tmp.log 2>&1
+  timeout 300 python bench.py --steps $1 --warmup 3 --lanes $2 $3 --no-cpu-baseline --no-kernel-breakdown --no-reference-cuda > gpurun_out/bench_tmp.log 2>&1
   python - "$@" <<'PY'
-import json,sys
+import json,sys,os
 l=[x for x in open('gpurun_out/bench_tmp.log') if x.startswith('{')]
 if l:
-    d=json.loads(l[-1]); print('lanes %s fps_sms %s -> %s'%(sys.argv[1],sys.argv[2],d['config'].get('sm_partition')),'value %.0f scenes/s  %.3f ms/step | e2e %.0f  %.2f ms/step'%(d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e']['ms_per_step']))
-    for r in d.get('roofline_kernels',[]):
-        if r['kernel'].startswith('fps'): print('   ',r['kernel'], round(r['us'],1),'us', '%.2f M rounds/s'%(r['rounds_per_s']/1e6))
-else: print(open('gpurun_out/bench_tmp.log').read()[-1500:])
+    d=json.loads(l[-1]); print('steps %s lanes %s %s'%(sys.argv[1],sys.argv[2],sys.argv[3:]),'value %.0f scenes/s  %.3f ms/step, host enqueue %.3f ms/step | e2e %.0f'%(d['value'],d['ms_per_step'],d['host_enqueue_ms_per_step'],d['e2e']['value']))
+else: print(open('gpurun_out/bench_tmp.log').read()[-2500:])
 PY
 }
-run 1 0; run 6 0 --no-kernel-breakdown; run 8 0 --no-kernel-breakdown; run 8 80 --no-kernel-breakdown; run 12 96 --no-kernel-breakdown
+run 50 8 --no-graphs; run 50 1; run 50 4; run 50 6; run 50 8; run 50 12; run 20 8; run 100 8

@@ -174,3 +174,13 @@ def test_signatures_match_reference():
     b = my_mod.PointnetSAModuleVotes(npoint=8, radius=0.3, nsample=4, mlp=[5, 8, 16])
     assert {k: tuple(v.shape) for k, v in a.state_dict().items()} == \
            {k: tuple(v.shape) for k, v in b.state_dict().items()}
+
+
+def test_split_first_layer_rule():
+    """Host logic of the split first SA layer: taken only where it shrinks the fused kernel's layer-1 K."""
+    from situation3d_b200 import fused
+    assert fused.split_first_layer(129, 64)        # SA1: K 144 -> 80
+    assert not fused.split_first_layer(128, 128)   # SA2: 144 -> 144
+    assert fused.split_first_layer(256, 128)       # SA3 / SA4: 272 -> 144
+    assert not fused.split_first_layer(129, 96)    # widths the per-point GEMM does not cover
+    assert not fused.split_first_layer(6, 64)

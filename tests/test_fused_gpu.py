@@ -335,3 +335,54 @@ def test_training_step_config4_single_gpu():
     assert all(not torch.equal(a, b) for a, b in zip(before, net.parameters()))
     for p_, v in zip(net.parameters(), tr.bucket.views):
         assert p_.grad.data_ptr() == v.data_ptr()
+
+
+def test_launch_count_and_sm_partition():
+    """pn2_launch_count counts this library's kernels (23 per bf16 backbone step of the bench shape family), and
+    running the sampling chains / the rest on two SM partitions (CUDA green contexts) changes nothing in the results."""
+    from situation3d_b200._lib import lib
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.streams import SmPartition
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=129, precision="bf16")).eval().cuda()
+    pc = torch.from_numpy(make_batch(2, 40000, 129, first_seed=7)).cuda()
+    with torch.no_grad():
+        want = net({"point_clouds": pc})
+        torch.cuda.synchronize()
+        n0 = lib.pn2_launch_count()
+        net({"point_clouds": pc})
+        torch.cuda.synchronize()
+        assert lib.pn2_launch_count() - n0 == 23
+        part = SmPartition(64)
+        assert part.sms[0] >= 64 and part.sms[0] + part.sms[1] <= 148 and part.sms[1] > 0
+        net.sm_partition = part
+        net._side_streams.clear()
+        lane = part.stream(part.MAIN)
+        assert lib.pn2_stream_sm_count(lane.cuda_stream) == part.sms[1]
+        lane.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(lane):
+            got = net({"point_clouds": pc})
+        lane.synchronize()
+    for k in ("sa1_inds", "sa4_inds", "fp2_inds"):
+        assert torch.equal(got[k], want[k])
+    assert torch.equal(got["fp2_features"], want["fp2_features"])
+
+
+def test_graphed_backbone_matches_eager():
+    """CUDA-graph replay of the step (both streams captured) returns what the eager call returns, for new inputs too."""
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.graphs import GraphedBackbone
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=129, precision="bf16")).eval().cuda()
+    pcs = [torch.from_numpy(make_batch(2, 40000, 129, first_seed=s)).cuda() for s in (3, 5)]
+    with torch.no_grad():
+        want = [{k: v.clone() for k, v in net({"point_clouds": pc}).items() if k != "point_clouds"} for pc in pcs]
+        step = GraphedBackbone(net, pcs[0])
+        assert step.launches_per_replay == 23
+        for pc, w in zip(pcs, want):
+            out = step(pc)
+            step.stream.synchronize()
+            for k in ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds", "fp2_xyz", "fp2_features", "sa1_features"):
+                assert torch.equal(out[k], w[k]), k
