@@ -310,6 +310,31 @@ def reference_cuda_arm(pc, sd, steps=3):
                     "max_pool2d (cuDNN), fp32 (TF32 conv default), B=%d, 1 GPU" % pc.shape[0]}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated, so
+    that the staging buffers of the end-to-end loop are first-touched on the GPU's NUMA node (with 8 ranks the H2D
+    copies otherwise cross the socket interconnect).  Returns the previous affinity (restored for the CPU baseline)."""
+    try:
+        import pynvml
+        import torch
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        try:
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1} & prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return prev, len(cpus)
+    except Exception:
+        return None, 0
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -319,6 +344,7 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    prev_affinity, numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else (None, 0)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     precision = args.precision or ("bf16" if "bf16" in fused.SA_FORWARD else "fp32")
@@ -470,6 +496,8 @@ def run_ours(args, rank, local_rank, world):
             except Exception as ex:   # test infrastructure must not take the bench down
                 ref_cuda = {"unavailable": repr(ex)[:200]}
             if not args.no_cpu_baseline:
+                if prev_affinity:
+                    os.sched_setaffinity(0, prev_affinity)      # the CPU baseline gets every host core again
                 from oracle import pn2_oracle as orc
                 cores = os.cpu_count() or 1
                 torch.set_num_threads(cores)
@@ -497,7 +525,9 @@ def run_ours(args, rank, local_rank, world):
                            "l2": "each input batch is %.0f MB (> 126 MB L2); two batches alternate" % (in_bytes / 1e6)},
                 "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "ms_per_step": 1e3 * dt_e2e / K,
                         "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                        "api": "Pointnet2Backbone.forward(data_dict) on pinned host point_clouds"},
+                        "api": "Pointnet2Backbone.forward(data_dict) on pinned host point_clouds",
+                        "host_numa_binding": "rank pinned to its GPU's %d local CPUs before allocating pinned buffers" % numa_cpus
+                                             if numa_cpus else None},
                 "gpu_launches": launches * world, "gpu_launches_per_step": launches / K,
                 "host_enqueue_ms_per_step": host_ms_per_step, "clocks": clocks, "peaks": pk}
         if rows:

@@ -15,4 +15,22 @@ with open('profiles/r1_multi_gpu.md', 'w') as f:
     f.write("The 2.6 MB gradient all-reduce takes %.0f us alone and is enqueued on a side stream after backward; step time is "
             "unchanged from 1 to 2 GPUs (%.2f -> %.2f ms), i.e. weak scaling of the training step is %.2fx at 2 GPUs.\n"
             % (t2['allreduce_us_alone'], t1['ms_per_step'], t2['ms_per_step'], t2['scenes_per_s'] / t1['scenes_per_s']))
-print(open('profiles/r1_multi_gpu.md').read()[:600])
+import os
+rows = []
+for n, path in ((1, 'profiles/r1_bench_1gpu.json'), (2, 'gpurun_out/bench_2gpu.log'), (4, 'gpurun_out/bench_4gpu.log'), (8, 'gpurun_out/bench_8gpu.log')):
+    if os.path.exists(path):
+        l = [x for x in open(path) if x.startswith('{')]
+        if l:
+            r = json.loads(l[-1])
+            rows.append((n, r['value'], r['ms_per_step'], r['e2e']['value']))
+if rows:
+    with open('profiles/r1_multi_gpu.md', 'a') as f:
+        f.write("\n## Scaling of bench.py on one box (scene-sharded, no collective; separate gpurun calls)\n\n"
+                "| GPUs | value (scenes/s, inputs in HBM) | ms/step | x of 1 GPU | e2e (scenes/s, host buffers) | H2D GB/s aggregate |\n|---|---|---|---|---|---|\n")
+        v1 = rows[0][1]
+        for n, v, ms, e in rows:
+            f.write("| %d | %.0f | %.3f | %.2f | %.0f | %.0f |\n" % (n, v, ms, v / v1, e, e / 8 * 168.96e6 / 1e9))
+        f.write("\nThe forward path scales linearly (no collective, no shared state).  `e2e` is bound by the host side: one GPU's "
+                "PCIe link at 1-2 GPUs (54 GB/s each), the box's aggregate host-to-device bandwidth (~170 GB/s on this "
+                "single-NUMA-node VM, `nvidia-smi topo`: all GPUs on CPUs 0-31) from 4 GPUs on.\n")
+print(open('profiles/r1_multi_gpu.md').read()[-1200:])
