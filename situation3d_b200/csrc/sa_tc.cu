@@ -28,6 +28,11 @@
 // tile into the part of the gather buffer that layer 1 has released.
 //
 // Precision: bf16 operands, fp32 accumulation (kind::f16); indices come from the fp32 kernels.
+//
+// Two kernels implement that chain.  sa_tc_kernel (below) runs a tile's gather, three MMA batches and three
+// epilogues strictly in sequence with 128 threads: any supported width / nsample, the reference for the
+// arithmetic.  sa_tc_v3_kernel (further down) is the software-pipelined one the backbone's shapes run on:
+// several tiles in flight, one warp role per pipeline stage, layer-2 activations kept in TMEM.
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -160,7 +165,6 @@ __global__ void pack_weights_kernel(SaTcShape s, const float *__restrict__ w1, c
 struct SaTcParams {
     SaTcShape s;
     int n, npoint, tiles_per_scene, ntiles;
-    int nstage;             // gather ring depth of the warp-specialised kernel (2..4)
     int nregion, nslot;     // pipelined kernel: shared-memory tile regions (<= 8) and TMEM accumulator slots (2 or 4)
     uint32_t blk;
     int debug;              // diagnostics (PN2_SA_TC_DEBUG): 1 skip the feature gather, 4 skip E2's proxy fence, 32 gather rows 0..127
@@ -401,239 +405,10 @@ sa_tc_kernel(const SaTcParams p)
     if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
-// ---- warp-specialised variant: gather warps run one tile ahead of the MMA / epilogue warps -----------
-// Same arithmetic as sa_tc_kernel.  The serial kernel above spends most of a tile waiting for the
-// gather (index load -> row addresses -> cp.async -> L2/HBM latency).  Here warps 4-7 only gather, into
-// a two-stage ring, and warps 0-3 only compute; a stage is handed over with mbarriers
-// (full: 128 producer arrivals after cp.async.wait_all + fence.proxy.async; empty: the tcgen05.commit
-// that follows the tile's last MMA).  Activations of layers 1 and 2 overwrite the stage the tile was
-// gathered into, so the ring needs no extra buffer.  Used when W1+W2+W3 and two stages fit in shared memory.
 __device__ __forceinline__ void tc_mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-constexpr int kPipeConsumers = 256;                 // warps 0-7: MMA issue + epilogues
-constexpr int kPipeProducers = 128;                 // warps 8-11: gather
-constexpr int kPipeThreads = kPipeConsumers + kPipeProducers;
-constexpr int kMaxStages = 4;
-
-template <int NS, int TMEM_COLS>
-__global__ void __launch_bounds__(kPipeThreads, 1)
-sa_tc_pipe_kernel(const SaTcParams p)
-{
-    extern __shared__ unsigned char smem_raw[];
-    const SaTcShape &s = p.s;
-    const uint32_t raw = smem_u32(smem_raw);
-    unsigned char *base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    const uint32_t resident = s.w1_bytes + s.w2_bytes + s.w3_bytes;
-    unsigned char *w1s = base, *w2s = base + s.w1_bytes, *w3s = base + s.w1_bytes + s.w2_bytes;
-    unsigned char *ring = base + resident;                                   // nstage stages of region_bytes
-    float *bias2 = reinterpret_cast<float *>(ring + p.nstage * s.region_bytes);
-    float *bias3 = bias2 + s.c2;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(bias3 + s.c3);            // full[4], empty[4], mma
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 9);
-    const int nstage = p.nstage;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.image);
-        for (uint32_t i = tid; i < resident / 16; i += kPipeThreads) cp_async16(smem_u32(base) + i * 16, src + i);
-        const float *bsrc = reinterpret_cast<const float *>(p.image + resident);
-        for (int i = tid; i < s.c2 + s.c3; i += kPipeThreads) bias2[i] = __ldg(bsrc + i);
-        if (tid == 0) {
-            for (int i = 0; i < kMaxStages; ++i) {
-                // full: per producer thread one arrival when its cp.asyncs have landed + one explicit (release)
-                tc_mbar_init(smem_u32(mbar + i), 2 * kPipeProducers);
-                tc_mbar_init(smem_u32(mbar + kMaxStages + i), 1);   // empty: one tcgen05.commit
-            }
-            tc_mbar_init(smem_u32(mbar + 2 * kMaxStages), 1);       // MMA -> epilogue
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
-        cp_async_wait_all();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-    }
-    const uint32_t tmem = *tmem_slot;
-    const int nchunk = s.row_elems / 8, xchunk = nchunk, k0chunks = s.k0 / 8;
-
-    if (warp >= kPipeConsumers / 32) {
-        // ===== gather warps =====
-        // Two lanes share a row: lane pair (2j, 2j+1) of producer thread ptid copies the even / odd 16-byte
-        // chunks of rows ptid/2 and ptid/2 + 64, so one cp.async instruction moves 32 contiguous bytes of 16
-        // rows (whole L2 sectors) and every thread's work is a flat, independent list of copies.
-        const int ptid = tid - kPipeConsumers;
-        const int sub = ptid & 1, r0 = ptid >> 1, r1 = r0 + 64;
-        const uint32_t sw0 = (uint32_t)(r0 & 7), sw1 = (uint32_t)(r1 & 7);
-        const int nfull8 = (s.k0 / 64) * 8;                      // chunks that live in 128B-swizzled tiles
-        int it = 0;
-        long long pc[4] = {0, 0, 0, 0}, tprev = 0;
-        const bool profiling = p.prof != nullptr && blockIdx.x == 0 && ptid == 0;
-        if (profiling) tprev = clock64();
-#define PN2_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
-        // neighbour indices of this thread's two rows, fetched one tile ahead
-        int nb0_next = 0, nb1_next = 0;
-        if ((int)blockIdx.x < p.ntiles) {
-            const int bi0 = blockIdx.x / p.tiles_per_scene;
-            const int *ip = p.idx + (size_t)bi0 * p.npoint * NS + (blockIdx.x - bi0 * p.tiles_per_scene) * kTile;
-            nb0_next = __ldg(ip + r0); nb1_next = __ldg(ip + r1);
-        }
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            const int st = it % nstage, u = it / nstage;
-            const int nb0 = nb0_next, nb1 = nb1_next;
-            {
-                const int nt = tile + gridDim.x;
-                if (nt < p.ntiles) {
-                    const int bn = nt / p.tiles_per_scene;
-                    const int *ip = p.idx + (size_t)bn * p.npoint * NS + (nt - bn * p.tiles_per_scene) * kTile;
-                    nb0_next = __ldg(ip + r0); nb1_next = __ldg(ip + r1);
-                }
-            }
-            if (u > 0) tc_mbar_wait(smem_u32(mbar + kMaxStages + st), (u - 1) & 1);   // the tile that used this stage is done
-            PN2_MARK(0)
-            unsigned char *region = ring + st * s.region_bytes;
-            const uint32_t a_base = smem_u32(region);
-            const int bi = tile / p.tiles_per_scene;
-            const int row0 = (tile - bi * p.tiles_per_scene) * kTile;
-            const int centre0 = row0 / NS;
-            const __nv_bfloat16 *src0 = p.table + ((size_t)bi * p.n + nb0) * s.row_elems;
-            const __nv_bfloat16 *src1 = p.table + ((size_t)bi * p.n + nb1) * s.row_elems;
-            // no wait here: the stage's "full" barrier fires when the copies land, so the gather warps run
-            // up to nstage tiles ahead of the tensor core
-#pragma unroll 4
-            for (int ch = sub; ch < nchunk; ch += 2) {
-                uint32_t o0, o1;
-                if (ch < nfull8) {
-                    const uint32_t t = (uint32_t)(ch >> 3) * (kTile * 128u);
-                    o0 = t + r0 * 128u + ((((uint32_t)ch & 7u) ^ sw0) << 4);
-                    o1 = t + r1 * 128u + ((((uint32_t)ch & 7u) ^ sw1) << 4);
-                } else {
-                    o0 = kop_chunk_off(kTile, s.k0, r0, ch);
-                    o1 = kop_chunk_off(kTile, s.k0, r1, ch);
-                }
-                cp_async16(a_base + o0, src0 + ch * 8);
-                cp_async16(a_base + o1, src1 + ch * 8);
-            }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar + st)) : "memory");
-            PN2_MARK(1)
-            {
-                // xyz chunk (+ zero padding) of one of the two rows per lane of the pair
-                const int row = sub ? r1 : r0, nb = sub ? nb1 : nb0;
-                const float *pp = p.xyz + ((size_t)bi * p.n + nb) * 3;
-                const float *cc = p.new_xyz + ((size_t)bi * p.npoint + centre0 + row / NS) * 3;
-                float h[3], l[3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float d = __fmul_rn(__fsub_rn(__ldg(pp + a), __ldg(cc + a)), p.inv_radius);
-                    h[a] = __bfloat162float(__float2bfloat16_rn(d));
-                    l[a] = d - h[a];
-                }
-                *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, row, xchunk)) =
-                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], l[0]), pack_bf16(l[1], l[2]), pack_bf16(1.f, 1.f));
-                for (int ch = xchunk + 1; ch < k0chunks; ++ch)
-                    *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, s.k0, row, ch)) = make_uint4(0u, 0u, 0u, 0u);
-            }
-            fence_proxy_async();
-            tc_mbar_arrive(smem_u32(mbar + st));                                   // release of the xyz chunk
-            PN2_MARK(2)
-        }
-        cp_async_wait_all();
-        if (profiling) { for (int i = 0; i < 3; ++i) p.prof[8 + i] = pc[i]; p.prof[11] = it; }
-#undef PN2_MARK
-    } else {
-        // ===== MMA + epilogue warps: warp w works on TMEM lanes 32*(w%4).. and on column half w/4 =====
-        const int quarter = warp & 3, half = warp >> 2;
-        const int row = quarter * 32 + lane;                                    // TMEM lane = sample row / channel
-        const uint32_t my_tmem = tmem + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t idesc1 = umma_idesc(kTile, s.c1), idesc2 = umma_idesc(kTile, s.c2), idesc3 = umma_idesc(128, kTile);
-        const uint32_t mma_bar = smem_u32(mbar + 2 * kMaxStages);
-        const uint32_t w1_base = smem_u32(w1s), w2_base = smem_u32(w2s), w3_base = smem_u32(w3s);
-        // column ranges of this warp's half (multiples of 32)
-        const int h1 = ((s.c1 / 2 + 31) / 32) * 32, h2 = ((s.c2 / 2 + 31) / 32) * 32;
-        const int c1_lo = half ? h1 : 0, c1_hi = half ? s.c1 : min(h1, s.c1);
-        const int c2_lo = half ? h2 : 0, c2_hi = half ? s.c2 : min(h2, s.c2);
-        // layer 3: the 128 sample columns split at 64 when a centre's samples do not straddle the split
-        const int s_lo = NS <= 64 ? half * 64 : 0, s_hi = NS <= 64 ? half * 64 + 64 : (half ? 0 : kTile);
-        uint32_t phase = 0;
-        int it = 0;
-        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
-        const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
-        if (profiling) tprev = clock64();
-#define PN2_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            const int st = it % nstage, u = it / nstage;
-            unsigned char *region = ring + st * s.region_bytes;
-            const uint32_t a_base = smem_u32(region);
-            const int bi = tile / p.tiles_per_scene;
-            const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
-            tc_mbar_wait(smem_u32(mbar + st), u & 1);                          // gathered
-            PN2_MARK(0)
-            fence_proxy_async();          // the gather's cp.async / st.shared writes -> visible to the tensor core
-            tc_fence_after();
-            if (warp == 0) {
-                const uint32_t elected = elect_one();
-                issue_gemm(tmem, a_base, kTile, 0, w1_base, s.c1, 0, s.k0, idesc1, elected);
-                if (elected) umma_commit(mma_bar);
-                __syncwarp();
-            }
-            tc_mbar_wait(mma_bar, phase); phase ^= 1;
-            tc_fence_after();
-            PN2_MARK(1)
-            epilogue_act(my_tmem, region, s.c1, row, c1_lo, c1_hi, nullptr);
-            tc_fence_before();
-            fence_proxy_async();
-            named_bar_sync(1, kPipeConsumers);
-            PN2_MARK(2)
-            if (warp == 0) {
-                tc_fence_after();
-                const uint32_t elected = elect_one();
-                issue_gemm(tmem, a_base, kTile, 0, w2_base, s.c2, 0, s.c1, idesc2, elected);
-                if (elected) umma_commit(mma_bar);
-                __syncwarp();
-            }
-            tc_mbar_wait(mma_bar, phase); phase ^= 1;
-            tc_fence_after();
-            PN2_MARK(3)
-            epilogue_act(my_tmem, region, s.c2, row, c2_lo, c2_hi, bias2);
-            tc_fence_before();
-            fence_proxy_async();
-            named_bar_sync(1, kPipeConsumers);
-            PN2_MARK(4)
-            if (warp == 0) {
-                tc_fence_after();
-                const uint32_t elected = elect_one();
-                for (int mt = 0; mt < s.c3 / 128; ++mt)
-                    issue_gemm(tmem + mt * kTile, w3_base, s.c3, mt * 128, a_base, kTile, 0, s.c2, idesc3, elected);
-                if (elected) {
-                    umma_commit(mma_bar);
-                    umma_commit(smem_u32(mbar + kMaxStages + st));              // stage free for the gather warps
-                }
-                __syncwarp();
-            }
-            tc_mbar_wait(mma_bar, phase); phase ^= 1;
-            tc_fence_after();
-            PN2_MARK(5)
-            if (s_lo < s_hi)
-                for (int mt = 0; mt < s.c3 / 128; ++mt)
-                    epilogue_pool<NS>(p, my_tmem + mt * kTile, bi, centre0, mt * 128 + row, bias3[mt * 128 + row], s_lo, s_hi);
-            tc_fence_before();
-            named_bar_sync(1, kPipeConsumers);   // every epilogue warp is done with TMEM before the next tile's MMA
-            PN2_MARK(6)
-        }
-        if (profiling) { for (int i = 0; i < 7; ++i) p.prof[i] = pc[i]; p.prof[7] = it; }
-#undef PN2_MARK
-    }
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
-}
-
 
 // ---- software-pipelined variant: several tiles in flight through the three layers --------------------
 // The kernels above run a tile's chain  gather -> MMA1 -> epi1 -> MMA2 -> epi2 -> MMA3 -> epi3  strictly in
@@ -1191,14 +966,8 @@ static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
 {
     const SaTcParams &p = p_in;
     const int sms = stream_sm_count(stream);
-    // warp-specialised two-stage variant when the resident weights and two gather stages fit
-    const uint32_t pipe_fixed = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + p.s.bias_bytes + 128u;
-    const uint32_t budget = 226u * 1024u;
-    int nstage = pipe_fixed < budget ? (int)((budget - pipe_fixed) / p.s.region_bytes) : 0;
-    nstage = min(nstage, kMaxStages);
-    if (const char *e = getenv("PN2_SA_TC_STAGES")) nstage = min(nstage, atoi(e));
-    const uint32_t pipe_smem = pipe_fixed + (uint32_t)max(nstage, 0) * p.s.region_bytes;
     {
+        // software-pipelined kernel for the instantiated shapes (PN2_SA_TC_V2=0 forces the serial kernel)
         const char *e2 = getenv("PN2_SA_TC_V2");
         const int R = v3_regions(p.s);
         const int T = p.s.c3 > 128 ? 2 : 4;
@@ -1212,24 +981,6 @@ static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
             const int grid = min(p.ntiles, sms);
             return dispatch_v3<NS>(q, grid, smem2, stream);
         }
-    }
-    const char *force = getenv("PN2_SA_TC_PIPE");
-    const bool want_pipe = force ? atoi(force) != 0 : true;
-    if (want_pipe && !p.s.w3_streamed && nstage >= 2) {
-        SaTcParams p = p_in;
-        p.nstage = nstage;
-        const int grid = min(p.ntiles, sms);
-        if (p.s.tmem_cols == 128) {
-            auto kern = sa_tc_pipe_kernel<NS, 128>;
-            PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
-            kern<<<grid, kPipeThreads, pipe_smem, stream>>>(p);
-        } else {
-            auto kern = sa_tc_pipe_kernel<NS, 256>;
-            PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
-            kern<<<grid, kPipeThreads, pipe_smem, stream>>>(p);
-        }
-        PN2_LAUNCH_CHECK("sa_tc_forward(pipe)");
-        return PN2_OK;
     }
     const int per_sm = max(1, min((int)((227u * 1024u) / (p.s.smem_bytes + 1024u)), 512 / p.s.tmem_cols));
     const int grid = min(p.ntiles, sms * per_sm);
@@ -1338,7 +1089,7 @@ extern "C" int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, i
     p.image = static_cast<const unsigned char *>(weight_image);
     p.out = out;
     p.out_table = static_cast<__nv_bfloat16 *>(out_table);
-    p.nstage = 0; p.nregion = 0; p.nslot = 0; p.blk = 0;
+    p.nregion = 0; p.nslot = 0; p.blk = 0;
     { const char *ed = getenv("PN2_SA_TC_DEBUG"); p.debug = ed ? atoi(ed) : 0; }
     p.prof = g_sa_tc_prof;
     switch (nsample) {
