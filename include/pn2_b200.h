@@ -222,6 +222,23 @@ int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, int c1, int 
                       const int *idx, const void *known_rows, const void *skip_rows,
                       const void *weight_image, float *out, void *out_rows, pn2_stream_t stream);
 
+/* ---- visual-token construction in front of the re-encoding (csrc/tokens.cu) ----
+ * Replaces the per-scene loop of SIG3D.forward, situation3d/models/sqa_module.py:297-315.
+ * pn2_column_pool: scene s owns voxels offsets[s] .. offsets[s+1] of coords (M,3) i32 / feats (M,c) f32 (all
+ *   device pointers, offsets (b+1) i32).  Its unique (x,y) columns, in the ascending order of
+ *   torch.unique(dim=0) (:298-299), go to rows offsets[s] .. offsets[s] + ncols[s] of out_coords (M,2) /
+ *   out_feats (M,c), with out_feats = sum over the column's voxels / (count + 1) -- scatter_reduce_('mean') onto a
+ *   zero tensor counts the zero (:300-301).  inverse (M) (may be NULL) = return_inverse.  At most
+ *   pn2_column_pool_max_voxels() voxels per scene, |x|,|y| < 2^19 (else *status = 1).
+ * pn2_token_gather: tokens[s,j,:] = pooled[offsets[s] + sampled[s,j], :], positions[s,j,:] =
+ *   (pooled_coords + stride/2) * voxel_size in fp32 as torch evaluates :311; the caller draws `sampled` (:303-308). */
+int pn2_column_pool_max_voxels(void);
+int pn2_column_pool(int b, const int *offsets, const int *coords, const float *feats, int c, int *ncols,
+                    int *out_coords, float *out_feats, int *inverse, int *status, pn2_stream_t stream);
+int pn2_token_gather(int b, int t, int c, const int *offsets, const int *sampled, const float *pooled,
+                     const int *pooled_coords, float half_x, float half_y, float voxel_size, float *tokens,
+                     float *positions, pn2_stream_t stream);
+
 /* ---- SM partitions for callers that keep several batches in flight (csrc/sm_partition.cu) ----------
  * The sampling chain of a batch is a latency-bound kernel of half-SM CTAs that lives ~2 ms; the fused MLP
  * kernels are persistent whole-SM CTAs.  pn2_sm_partition_create splits the current device's SMs into a first

@@ -305,3 +305,27 @@ def reencode(tokens, positions, situation, w1, b1, w2, b2, to_agent_frame=False,
     wgt = torch.exp(-dist ** 2 / (2 * sigma ** 2))
     prior = wgt / wgt.sum(dim=1, keepdim=True)
     return out, new_pos, prior
+
+
+# ---- visual-token construction ---------------------------------------
+def column_tokens(coords_list, feats_list, tensor_stride, num_points=256, voxel_size=0.02):
+    """situation3d/models/sqa_module.py:297-317 restated with the same PyTorch (CPU) calls in the same order, RNG
+    calls included: unique (x, y) columns (:298-299), scatter_reduce_('mean') onto zeros, i.e. sum / (count + 1)
+    (:300-301), randperm / randint sampling (:303-308), positions in metres (:311).
+    Returns (scene_feat (B,T,C), scene_positions (B,T,2), [unique_coords], [reduced_feats], [inverse])."""
+    scene_feat, scene_positions, uniq, red, inv = [], [], [], [], []
+    for coords, feats in zip(coords_list, feats_list):
+        reduced_coords = coords[:, [0, 1]]
+        unique_coords, indices = reduced_coords.unique(dim=0, return_inverse=True)
+        reduced_feats = torch.zeros(unique_coords.size(0), feats.size(1))
+        reduced_feats = reduced_feats.scatter_reduce_(0, indices.unsqueeze(-1).expand_as(feats), feats, reduce='mean')
+        if num_points < unique_coords.size(0):
+            sampled = torch.randperm(unique_coords.size(0))[:num_points]
+        else:
+            sampled = torch.cat([torch.randperm(unique_coords.size(0)),
+                                 torch.randint(0, unique_coords.size(0), (num_points - unique_coords.size(0),))])
+        positions = (unique_coords[sampled] + torch.tensor(tensor_stride[0:2]) / 2) * voxel_size
+        scene_feat.append(reduced_feats[sampled].unsqueeze(0))
+        scene_positions.append(positions.unsqueeze(0))
+        uniq.append(unique_coords); red.append(reduced_feats); inv.append(indices)
+    return torch.cat(scene_feat, dim=0), torch.cat(scene_positions, dim=0), uniq, red, inv

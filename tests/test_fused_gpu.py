@@ -386,3 +386,42 @@ def test_graphed_backbone_matches_eager():
             step.stream.synchronize()
             for k in ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds", "fp2_xyz", "fp2_features", "sa1_features"):
                 assert torch.equal(out[k], w[k]), k
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_column_tokens_vs_reference_loop(name):
+    """Token construction (csrc/tokens.cu) against the outputs of the reference's own loop (sqa_module.py:297-315,
+    executed unmodified by tests/golden/make_ref_token_goldens.py) with the same RNG seed: the sampled columns and
+    their positions are identical, the pooled features equal the reference's sum / (count + 1)."""
+    import os
+    from situation3d_b200 import tokens
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_tokens.npz"))
+    n = int(g[name + "_nscenes"])
+    coords = [torch.from_numpy(g["%s_coords%d" % (name, i)]) for i in range(n)]
+    feats = [torch.from_numpy(g["%s_feats%d" % (name, i)]) for i in range(n)]
+    torch.manual_seed(1234)
+    want_tok, want_pos, uniq, red, inv = orc.column_tokens(coords, feats, [16, 16, 16], 256, 0.02)
+    assert torch.equal(want_tok, torch.from_numpy(g[name + "_scene_feat"]))         # oracle == reference (CPU suite too)
+    cc, ff = [c.cuda() for c in coords], [f.cuda() for f in feats]
+    offsets, ncols, pc, pf, inverse = tokens.column_pool(cc, ff)
+    off = offsets.cpu().tolist()
+    for s in range(n):
+        assert ncols[s] == uniq[s].shape[0]
+        assert torch.equal(pc[off[s]:off[s] + ncols[s]].cpu(), uniq[s].to(torch.int32))      # torch.unique(dim=0) order
+        assert torch.equal(inverse[off[s]:off[s + 1]].cpu().long(), inv[s])                  # return_inverse
+        torch.testing.assert_close(pf[off[s]:off[s] + ncols[s]].cpu(), red[s], rtol=1e-6, atol=1e-7)
+    torch.manual_seed(1234)
+    tok, pos = tokens.column_tokens(cc, ff, [16, 16, 16], 256, 0.02)
+    assert torch.equal(pos.cpu(), torch.from_numpy(g[name + "_scene_positions"]))
+    torch.testing.assert_close(tok.cpu(), torch.from_numpy(g[name + "_scene_feat"]), rtol=1e-6, atol=1e-7)
+
+
+def test_column_pool_limits():
+    from situation3d_b200 import tokens
+    c = torch.zeros(4, 3, dtype=torch.int32, device="cuda")
+    c[0, 0] = 1 << 20
+    with pytest.raises(RuntimeError):
+        tokens.column_pool([c], [torch.zeros(4, 8, device="cuda")])
+    one = torch.tensor([[3, -5, 7]], dtype=torch.int32, device="cuda")
+    offsets, ncols, pc, pf, inv = tokens.column_pool([one], [torch.full((1, 8), 2.0, device="cuda")])
+    assert ncols == [1] and pc[0].tolist() == [3, -5] and torch.allclose(pf[0], torch.full((8,), 1.0, device="cuda"))

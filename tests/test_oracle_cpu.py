@@ -224,3 +224,28 @@ def test_situation_helpers_match_reference_python(ref_modules_golden):
     out_id, _, _ = orc.reencode(T(g["sit_tokens"]), T(g["sit_pos"]), ident, T(g["sit_pe_0.weight"]),
                                 T(g["sit_pe_0.bias"]), T(g["sit_pe_2.weight"]), T(g["sit_pe_2.bias"]))
     np.testing.assert_allclose(out_id.numpy(), g["sit_tokens_pe"], rtol=1e-5, atol=1e-5)
+
+
+def _token_case(g, name):
+    n = int(g[name + "_nscenes"])
+    coords = [torch.from_numpy(g["%s_coords%d" % (name, i)]) for i in range(n)]
+    feats = [torch.from_numpy(g["%s_feats%d" % (name, i)]) for i in range(n)]
+    return coords, feats
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_column_tokens_oracle_vs_reference_loop(name):
+    """The oracle's restatement of sqa_module.py:297-317 against the outputs of the reference's own loop (executed
+    unmodified by tests/golden/make_ref_token_goldens.py), RNG stream included: bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_tokens.npz"))
+    coords, feats = _token_case(g, name)
+    torch.manual_seed(1234)
+    tok, pos, uniq, red, inv = orc.column_tokens(coords, feats, [16, 16, 16], 256, 0.02)
+    assert torch.equal(tok, torch.from_numpy(g[name + "_scene_feat"]))
+    assert torch.equal(pos, torch.from_numpy(g[name + "_scene_positions"]))
+    # the quirk the CUDA path reproduces: scatter_reduce_('mean') onto zeros divides by count + 1
+    for c, f, u, r, iv in zip(coords, feats, uniq, red, inv):
+        cnt = torch.bincount(iv, minlength=u.shape[0]).float()
+        want = torch.zeros_like(r).index_add_(0, iv, f) / (cnt + 1)[:, None]
+        torch.testing.assert_close(r, want, rtol=1e-5, atol=1e-6)
