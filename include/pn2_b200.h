@@ -222,6 +222,16 @@ int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, int c1, int 
                       const int *idx, const void *known_rows, const void *skip_rows,
                       const void *weight_image, float *out, void *out_rows, pn2_stream_t stream);
 
+/* ---- the linear + GELU that consumes the visual tokens (csrc/head_tc.cu) -------
+ * SIG3D.scene_feat_linear = Sequential(Linear(256, 768), GELU()), situation3d/models/sqa_module.py:180-183,344:
+ * out (rows, n) f32 = GELU_erf(x (rows, k) f32 . W^T + bias) as one tcgen05 kernel (bf16 operands, fp32 accumulate).
+ * W (n, k) f32 -> image by pn2_linear_gelu_tc_pack_weights.  k multiple of 64, n multiple of 128. */
+int pn2_linear_gelu_tc_supported(int k, int n);
+size_t pn2_linear_gelu_tc_weight_image_bytes(int k, int n);
+int pn2_linear_gelu_tc_pack_weights(int k, int n, const float *w, void *image, pn2_stream_t stream);
+int pn2_linear_gelu_tc_forward(long long rows, int k, int n, const float *x, const void *weight_image,
+                               const float *bias, float *out, pn2_stream_t stream);
+
 /* ---- visual-token construction in front of the re-encoding (csrc/tokens.cu) ----
  * Replaces the per-scene loop of SIG3D.forward, situation3d/models/sqa_module.py:297-315.
  * pn2_column_pool: scene s owns voxels offsets[s] .. offsets[s+1] of coords (M,3) i32 / feats (M,c) f32 (all

@@ -79,6 +79,10 @@ _PROTOTYPES = {
     "pn2_fp_tc_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_debug_sa_tc_profile": (_i, [_p]),
     "pn2_selftest_umma": (_i, [_i, _i, _p, _p, _p, _p]),
+    "pn2_linear_gelu_tc_supported": (_i, [_i, _i]),
+    "pn2_linear_gelu_tc_weight_image_bytes": (c_size_t, [_i, _i]),
+    "pn2_linear_gelu_tc_pack_weights": (_i, [_i, _i, _p, _p, _p]),
+    "pn2_linear_gelu_tc_forward": (_i, [ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p]),
     "pn2_column_pool_max_voxels": (_i, []),
     "pn2_column_pool": (_i, [_i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "pn2_token_gather": (_i, [_i, _i, _i, _p, _p, _p, _p, _f, _f, _f, _p, _p, _p]),

@@ -425,3 +425,28 @@ def test_column_pool_limits():
     one = torch.tensor([[3, -5, 7]], dtype=torch.int32, device="cuda")
     offsets, ncols, pc, pf, inv = tokens.column_pool([one], [torch.full((1, 8), 2.0, device="cuda")])
     assert ncols == [1] and pc[0].tolist() == [3, -5] and torch.allclose(pf[0], torch.full((8,), 1.0, device="cuda"))
+
+
+@pytest.mark.parametrize("B,T,k,n", [(32, 256, 256, 768), (3, 50, 64, 128), (1, 1, 128, 256)])
+def test_scene_feat_linear_vs_torch(B, T, k, n):
+    """SIG3D.scene_feat_linear (Linear + exact GELU, sqa_module.py:180-183) as one tcgen05 kernel against the PyTorch
+    modules the reference runs: bf16 operands -> max|err| <= 2e-2 max|ref| (north_star's bf16 tolerance); state-dict keys
+    are the reference's."""
+    from situation3d_b200.heads import SceneFeatLinear
+    torch.manual_seed(3)
+    m = SceneFeatLinear(k, n).eval()
+    assert list(m.state_dict().keys()) == ["0.weight", "0.bias"]
+    x = torch.randn(B, T, k)
+    with torch.no_grad():
+        want = torch.nn.functional.gelu(torch.nn.functional.linear(x, m[0].weight, m[0].bias))
+        got = m.cuda()(x.cuda())
+        # tight check against the same product with bf16-rounded operands (what the kernel computes)
+        wq = torch.nn.functional.gelu(torch.nn.functional.linear(x.bfloat16().float(), m[0].weight.cpu().bfloat16().float(), m[0].bias.cpu()))
+    assert got.shape == (B, T, n)
+    assert float((got.cpu() - want).abs().max()) <= 2e-2 * float(want.abs().max())
+    torch.testing.assert_close(got.cpu(), wq, rtol=1e-4, atol=1e-4)
+    # training mode runs the reference's modules (autograd)
+    m.train()
+    y = m(x.cuda().requires_grad_())
+    y.sum().backward()
+    assert m[0].weight.grad is not None
