@@ -305,6 +305,15 @@ def test_situated_scene_encoder_config3():
     assert_features(d["scene_feat"], want_tok, "fp32")
     torch.testing.assert_close(d["scene_positions_agent"].cpu(), want_pos, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(d["auxiliary_task_loc_gt"].cpu(), want_prior, rtol=1e-3, atol=1e-7)
+    # VoteNet names of the seeds (lib/loss_helper.py:47-59) and, with hidden_size, SIG3D.scene_feat_linear on the tokens
+    assert d["seed_xyz"] is d["fp2_xyz"] and d["seed_inds"] is d["fp2_inds"] and d["seed_features"] is d["fp2_features"]
+    enc2 = SituatedSceneEncoder(129, 256, precision="bf16", hidden_size=768).eval().cuda()
+    with torch.no_grad():
+        d2 = enc2({"point_clouds": pc.cuda(), "auxiliary_task": sit.cuda()})
+        lin = enc2.scene_feat_linear[0]
+        want_h = torch.nn.functional.gelu(torch.nn.functional.linear(d2["scene_feat"], lin.weight, lin.bias))
+    assert d2["scene_feat_hidden"].shape == (2, 256, 768)
+    assert float((d2["scene_feat_hidden"] - want_h).abs().max()) <= 2e-2 * float(want_h.abs().max())
 
 
 def test_backbone_stress_config5_shape():
