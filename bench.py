@@ -401,7 +401,12 @@ def run_ours(args, rank, local_rank, world):
             # one captured step per lane (situation3d_b200.graphs): replaying it costs the host one cudaGraphLaunch
             # instead of ~0.8 ms of Python launches, which is what bounds the eager loop once lanes overlap
             from situation3d_b200.graphs import GraphedBackbone
-            graphs = [GraphedBackbone(net, pool[i % 2], stream=ln, static_input=pool[i % 2]) for i, ln in enumerate(lanes)]
+            try:
+                graphs = [GraphedBackbone(net, pool[i % 2], stream=ln, static_input=pool[i % 2]) for i, ln in enumerate(lanes)]
+            except Exception as ex:      # capture unavailable (e.g. under a profiler): same kernels, enqueued from Python
+                graphs, args.no_graphs = None, True
+                print("bench: CUDA-graph capture failed (%s); eager launches" % repr(ex)[:120], file=sys.stderr)
+                torch.cuda.synchronize()
 
         def run_steps(steps):
             for i in range(steps):
