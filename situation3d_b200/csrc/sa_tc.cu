@@ -882,7 +882,7 @@ template <int NS, int C1, int C2, int C3, int NCHUNK>
 static int launch_v3(const SaTcParams &q, int grid, uint32_t smem, cudaStream_t stream)
 {
     // the phase profile is compiled for the bench shapes only
-    constexpr bool kHasProf = (NS == 64 && C3 == 128) || (NS == 32 && NCHUNK == 17 && C3 == 256) || (NS == 16 && NCHUNK == 16);
+    constexpr bool kHasProf = (NS == 64 && C3 == 128) || (NS == 32 && C3 == 256) || (NS == 16 && NCHUNK == 16);
     if (kHasProf && q.prof) {
         auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, NCHUNK, kHasProf>;
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
