@@ -202,8 +202,13 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
         name = "sa%d" % (lvl + 1)
         inds, cxyz = fused.fps_with_xyz(src_xyz, m.npoint)
         t = timeit(lambda: fused.fps_with_xyz(src_xyz, m.npoint))
+        # FPS is a chain of dependent rounds: besides the (meaningless) HBM figure, report rounds/s and how much of the
+        # machine's FP32 issue rate the distance updates use (4 instructions per point-update: 3 packed sub/mul/fma
+        # pairs + min; 148 SMs x 128 lanes)
+        upd = B * (m.npoint - 1) * n_in / t
         rows.append({"kernel": "fps_" + name, "bound": "hbm", "seconds": t,
-                     "alg_bytes": B * (12 * n_in + 16 * m.npoint), "rounds_per_s": (m.npoint - 1) / t})
+                     "alg_bytes": B * (12 * n_in + 16 * m.npoint), "rounds_per_s": (m.npoint - 1) / t,
+                     "point_updates_per_s": upd, "fp32_issue_frac": upd * 4 / (148 * 128 * 1.965e9)})
         idx = fused.ball_query(src_xyz, cxyz, m.radius, m.nsample)
         t = timeit(lambda: fused.ball_query(src_xyz, cxyz, m.radius, m.nsample))
         rows.append({"kernel": "ball_query_" + name, "bound": "hbm", "seconds": t,
@@ -543,12 +548,16 @@ def run_ours(args, rank, local_rank, world):
                                 "traffic": traffic.get(dom["kernel"]),
                                 "share_of_step": dom["share"], "us_per_launch": dom["us"],
                                 "peak_source": pk["source"] + (" burst" if dom["bound"] == "tensor" else "")}
+            for extra in ("rounds_per_s", "point_updates_per_s", "fp32_issue_frac"):
+                if extra in dom:
+                    line["roofline"][extra] = dom[extra]
             if "rounds_per_s" in dom:
-                line["roofline"]["rounds_per_s"] = dom["rounds_per_s"]
+                line["roofline"]["note"] = ("latency chain of dependent argmax rounds: neither HBM nor the tensor pipe bounds it; "
+                                            "rounds_per_s is the figure of merit (DESIGN.md 4.1)")
             line["roofline_kernels"] = [
                 {k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()
                  if k in ("kernel", "bound", "us", "share", "achieved", "unit", "frac", "hbm_gbs", "rounds_per_s",
-                          "layer_tflops")}
+                          "fp32_issue_frac", "layer_tflops")}
                 for r in rows]
             for r in line["roofline_kernels"]:
                 if r["kernel"] in traffic:
