@@ -457,21 +457,33 @@ def run_ours(args, rank, local_rank, world):
         # ---- end to end: pinned host input -> H2D -> forward -> D2H of the result, double-buffered ----
         # each lane owns a device input buffer and pinned result buffers; its H2D copy, forward and D2H
         # copies are enqueued on the lane's stream, so lanes overlap each other's copies and kernels
-        dbuf = [pool[0].clone() for _ in lanes]
-        e2e_graphs = None
-        if not args.no_graphs and not args.no_e2e:
+        # ---- end to end through the public serving API (situation3d_b200.graphs.BackbonePipeline): per step a pinned
+        # host batch is copied to the lane's device buffer, the captured step is replayed and fp2_features / fp2_xyz /
+        # fp2_inds are copied back to pinned host memory, all on the lane's stream; `lanes` batches in flight
+        pipe, dbuf, res_host = None, None, None
+        if not args.no_e2e:
             graphs = None                                     # release the resident-run graphs' pools
-            e2e_graphs = [GraphedBackbone(net, pool[0], stream=ln, static_input=dbuf[i]) for i, ln in enumerate(lanes)]
-        res_host = [{k: torch.empty_like(out[k], device="cpu").pin_memory() for k in ("fp2_features", "fp2_xyz", "fp2_inds")}
-                    for _ in lanes]
-        out_bytes = sum(v.numel() * v.element_size() for v in res_host[0].values())
+            if not args.no_graphs:
+                from situation3d_b200.graphs import BackbonePipeline
+                pipe = BackbonePipeline(net, pool[0], streams=lanes)
+                in_bytes, out_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+            else:
+                dbuf = [pool[0].clone() for _ in lanes]
+                res_host = [{k: torch.empty_like(out[k], device="cpu").pin_memory() for k in ("fp2_features", "fp2_xyz", "fp2_inds")}
+                            for _ in lanes]
+                out_bytes = sum(v.numel() * v.element_size() for v in res_host[0].values())
+        else:
+            out_bytes = 0
 
         def e2e_loop(steps):
             for i in range(steps):
+                if pipe is not None:
+                    pipe.submit(host_pool[i % 2])
+                    continue
                 ln = i % len(lanes)
                 with torch.cuda.stream(lanes[ln]):
                     dbuf[ln].copy_(host_pool[i % 2], non_blocking=True)
-                    o = e2e_graphs[ln]() if e2e_graphs else net({"point_clouds": dbuf[ln]})
+                    o = net({"point_clouds": dbuf[ln]})
                     for k, v in res_host[ln].items():
                         v.copy_(o[k], non_blocking=True)
                     outs[ln] = o
@@ -535,7 +547,8 @@ def run_ours(args, rank, local_rank, world):
                            "l2": "each input batch is %.0f MB (> 126 MB L2); two batches alternate" % (in_bytes / 1e6)},
                 "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "ms_per_step": 1e3 * dt_e2e / K,
                         "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                        "api": "Pointnet2Backbone.forward(data_dict) on pinned host point_clouds",
+                        "api": "situation3d_b200.graphs.BackbonePipeline.submit(pinned host point_clouds) -> pinned host results"
+                               if not args.no_graphs else "Pointnet2Backbone.forward(data_dict) on pinned host point_clouds",
                         "host_numa_binding": "rank pinned to its GPU's %d local CPUs before allocating pinned buffers" % numa_cpus
                                              if numa_cpus else None},
                 "gpu_launches": launches * world, "gpu_launches_per_step": launches / K,

@@ -42,3 +42,56 @@ class GraphedBackbone:
                 self.static_in.copy_(pc, non_blocking=True)
             self.graph.replay()
         return self.out
+
+
+class BackbonePipeline:
+    """Several batches in flight from HOST buffers: the serving loop `bench.py` measures as ``e2e``.
+
+        pipe = BackbonePipeline(net, example_pc, lanes=8)       # one captured step + pinned result buffers per lane
+        for pc_host in loader:                                  # (B, N, 3+C) f32, ideally pinned
+            ticket = pipe.submit(pc_host)                       # H2D copy, graph replay, D2H of the results: all async
+            ...
+            out = pipe.result(ticket)                           # dict of pinned host tensors (waits for that batch only)
+
+    A lane is reused round robin: ``submit`` first waits for the lane's previous batch, so at most ``lanes`` batches
+    are in flight and a ticket's host buffers stay valid until ``lanes`` further submissions.
+    """
+
+    def __init__(self, net, example, lanes=8, outputs=("fp2_features", "fp2_xyz", "fp2_inds"), streams=None):
+        dev = example.device if example.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        example = example.to(dev)
+        self.streams = list(streams) if streams is not None else [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        self.inputs = [example.clone() for _ in self.streams]
+        self.steps = [GraphedBackbone(net, example, stream=st, static_input=buf) for st, buf in zip(self.streams, self.inputs)]
+        self.outputs = tuple(outputs)
+        self.host = [{k: torch.empty_like(s.out[k], device="cpu").pin_memory() for k in self.outputs} for s in self.steps]
+        self.done = [torch.cuda.Event() for _ in self.streams]
+        self._busy = [False] * len(self.streams)
+        self._next = 0
+        self.h2d_bytes = example.numel() * example.element_size()
+        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.host[0].values())
+
+    def submit(self, pc):
+        ln = self._next
+        self._next = (ln + 1) % len(self.streams)
+        if self._busy[ln]:
+            self.done[ln].synchronize()
+        with torch.cuda.stream(self.streams[ln]):
+            self.inputs[ln].copy_(pc, non_blocking=True)
+            out = self.steps[ln]()
+            for k, v in self.host[ln].items():
+                v.copy_(out[k], non_blocking=True)
+            self.done[ln].record()
+        self._busy[ln] = True
+        return ln
+
+    def result(self, ticket):
+        self.done[ticket].synchronize()
+        self._busy[ticket] = False
+        return self.host[ticket]
+
+    def drain(self):
+        for ln, busy in enumerate(self._busy):
+            if busy:
+                self.done[ln].synchronize()
+                self._busy[ln] = False

@@ -459,3 +459,31 @@ def test_scene_feat_linear_vs_torch(B, T, k, n):
     y = m(x.cuda().requires_grad_())
     y.sum().backward()
     assert m[0].weight.grad is not None
+
+
+def test_backbone_pipeline_from_host_buffers():
+    """BackbonePipeline (the serving loop bench.py times as e2e): batches submitted from pinned host memory come back
+    in pinned host memory, equal to the eager forward, with more submissions than lanes."""
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.graphs import BackbonePipeline
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=129, precision="bf16")).eval().cuda()
+    host = [torch.from_numpy(make_batch(2, 40000, 129, first_seed=s)).pin_memory() for s in (11, 12, 13, 14, 15)]
+    with torch.no_grad():
+        want = [{k: net({"point_clouds": h.cuda()})[k].cpu() for k in ("fp2_features", "fp2_xyz", "fp2_inds")} for h in host]
+        pipe = BackbonePipeline(net, host[0].cuda(), lanes=2)
+        assert pipe.h2d_bytes == host[0].numel() * 4
+        tickets = []
+        for i, h in enumerate(host):
+            if i >= 2:                                  # the lane is about to be reused: consume its previous result first
+                t_prev, j = tickets[i - 2]
+                got = pipe.result(t_prev)
+                for k in want[j]:
+                    assert torch.equal(got[k], want[j][k]), (j, k)
+            tickets.append((pipe.submit(h), i))
+        for t, j in tickets[-2:]:
+            got = pipe.result(t)
+            for k in want[j]:
+                assert torch.equal(got[k], want[j][k]), (j, k)
+        pipe.drain()
