@@ -510,6 +510,9 @@ def run_ours(args, rank, local_rank, world):
         barrier()
 
         rows, ref_cuda, cpu_base = None, None, None
+        if world > 1:
+            # the per-kernel breakdown, the CPU baseline and the reference-CUDA arm are single-GPU measurements
+            args.no_kernel_breakdown = args.no_reference_cuda = args.no_cpu_baseline = True
         if rank == 0:
             if not args.no_kernel_breakdown:
                 rows = kernel_breakdown(net, pool[0], precision, pk)
