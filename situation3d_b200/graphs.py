@@ -10,7 +10,8 @@ fixed input shape capture the step once and replay it:
     step.stream.synchronize()
 
 The graph holds both streams' work (fork / join through events), its tensors live in the graph's private memory
-pool, and ``out`` is the same dict of static output tensors on every call.
+pool, and ``out`` is the same dict of static output tensors on every call.  The capture also freezes the weight
+images of the fused layers: capture again after the module's parameters change.
 """
 import torch
 

@@ -38,7 +38,9 @@ class SceneFeatLinear(nn.Sequential):
                  and lin.bias is not None and not (torch.is_grad_enabled() and (x.requires_grad or lin.weight.requires_grad))
                  and lib.pn2_linear_gelu_tc_supported(k, n))
         if not fused:
-            return super().forward(x)
+            if not x.is_cuda:
+                raise RuntimeError("SceneFeatLinear: CUDA tensor required (this package has no CPU path)")
+            return super().forward(x)       # training / autograd, fp32 arm or widths outside the kernel: the reference's modules
         x2 = x.contiguous().view(-1, k)
         out = torch.empty((x2.shape[0], n), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
