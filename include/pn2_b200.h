@@ -125,6 +125,10 @@ int pn2_group_points_grad(int b, int c, int n, int npoints, int nsample, const f
  * every CTA already holds the winner's coordinates each round. */
 int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *idxs,
                                     float *new_xyz, pn2_stream_t stream);
+/* Same over rows of `pitch` >= 3 floats whose first three are x, y, z (the (b, n, 3+C) point_clouds tensor read in
+ * place); xyz_copy (b,n,3) or NULL receives the contiguous coordinates (written once while the points are loaded). */
+int pn2_furthest_point_sampling_rows(int b, int n, int m, const float *rows, int pitch, int *idxs,
+                                     float *new_xyz, float *xyz_copy, pn2_stream_t stream);
 
 /* Diagnostic: same launch as pn2_furthest_point_sampling; prof (device, 5 x int64) receives the SM cycles
  * thread 0 of CTA 0 spent per phase of a round, summed over the m-1 rounds. */

@@ -76,7 +76,9 @@ class Pointnet2Backbone(nn.Module):
         pc = pc.contiguous()
         dev = pc.device
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
-        xyz = pc[..., 0:3].contiguous()
+        # the contiguous (B, N, 3) coordinates are written by the first sampling kernel itself while it loads the
+        # points out of point_clouds (no separate copy kernel); everything that reads them runs after that kernel
+        xyz = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
         main = torch.cuda.current_stream(dev)
         # one sampling stream per caller stream: callers that keep several batches in flight (one stream
         # per batch) get independent sampling pyramids that overlap with each other's MLP kernels
@@ -95,7 +97,10 @@ class Pointnet2Backbone(nn.Module):
         with torch.cuda.stream(side):
             src = xyz
             for lvl, m in enumerate(sas):
-                _fused.fps_into(src, inds[lvl], cxyz[lvl])
+                if lvl == 0:
+                    _fused.fps_rows_into(pc, inds[0], cxyz[0], xyz)
+                else:
+                    _fused.fps_into(src, inds[lvl], cxyz[lvl])
                 ready[lvl].record(side)
                 src = cxyz[lvl]
 

@@ -169,8 +169,8 @@ __device__ __forceinline__ void take_later_if_greater(Cand &a, const Cand &b)
 // between the single-CTA exchange (shared memory + bar.sync) and the DSMEM exchange.
 template <int P, bool REGS, bool CLUSTER, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int *__restrict__ idxs,
-           float *__restrict__ new_xyz, long long *__restrict__ prof)
+fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int pitch, int *__restrict__ idxs,
+           float *__restrict__ new_xyz, float *__restrict__ xyz_copy, long long *__restrict__ prof)
 {
     static_assert(P % 2 == 0, "slots are processed in pairs");
     extern __shared__ float dyn[];   // sx[P*T], sy[P*T], sz[P*T]: the winner's coordinates are fetched from here
@@ -184,7 +184,8 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const uint32_t C = CLUSTER ? cluster_nctarank() : 1u, rank = CLUSTER ? cluster_ctarank() : 0u;
     const int scene = blockIdx.x / C;
-    const float *p = xyz + (size_t)scene * n * 3;
+    const float *p = xyz + (size_t)scene * n * pitch;       // rows of `pitch` floats, xyz first (pitch = 3: plain (n,3))
+    float *cp = xyz_copy ? xyz_copy + (size_t)scene * n * 3 : nullptr;   // optional contiguous (n,3) copy, written once
     int *out_idx = idxs + (size_t)scene * m;
     float *out_xyz = new_xyz ? new_xyz + (size_t)scene * m * 3 : nullptr;
     float *sx = dyn, *sy = dyn + P * T, *sz = dyn + 2 * P * T;
@@ -205,9 +206,10 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
             c[h][0] = c[h][1] = c[h][2] = 0.f;
             t[h] = -1.f;                                 // -1: never a candidate (fminf keeps it at -1)
             if (k >= 0) {
-                c[h][0] = __ldg(p + 3 * (size_t)k);
-                c[h][1] = __ldg(p + 3 * (size_t)k + 1);
-                c[h][2] = __ldg(p + 3 * (size_t)k + 2);
+                c[h][0] = __ldg(p + (size_t)pitch * k);
+                c[h][1] = __ldg(p + (size_t)pitch * k + 1);
+                c[h][2] = __ldg(p + (size_t)pitch * k + 2);
+                if (cp) { cp[3 * (size_t)k] = c[h][0]; cp[3 * (size_t)k + 1] = c[h][1]; cp[3 * (size_t)k + 2] = c[h][2]; }
                 // sampling_gpu.cu:100-101: float mag compared against the double literal 1e-3
                 if (!((double)sqnorm3(c[h][0], c[h][1], c[h][2]) <= 1e-3)) t[h] = 1e10f;   // sampling.cpp:74-76
             }
@@ -411,8 +413,8 @@ static bool make_plan(int n, FpsPlan *pl)
 }
 
 template <int P, bool REGS, int MAXT>
-static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
-                  long long *prof, cudaStream_t stream)
+static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int pitch, int *idxs, float *new_xyz,
+                  float *xyz_copy, long long *prof, cudaStream_t stream)
 {
     // large clusters of 256-thread CTAs: a second variant capped at 128 registers lets two CTAs share an SM
     // (twice the scenes in flight when several batches run concurrently)
@@ -436,16 +438,16 @@ static int launch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PN2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, n, m, pl.lg_bs, pl.cnt, xyz, idxs, new_xyz, prof));
+    PN2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, n, m, pl.lg_bs, pl.cnt, xyz, pitch, idxs, new_xyz, xyz_copy, prof));
     count_launches(1);
     return PN2_OK;
 }
 
-static int dispatch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int *idxs,
-                    float *new_xyz, long long *prof, cudaStream_t s)
+static int dispatch(const FpsPlan &pl, int b, int n, int m, const float *xyz, int pitch, int *idxs,
+                    float *new_xyz, float *xyz_copy, long long *prof, cudaStream_t s)
 {
 #define PN2_FPS_CASE(P, REGS, MAXT) \
-    case P: return launch<P, REGS, MAXT>(pl, b, n, m, xyz, idxs, new_xyz, prof, s)
+    case P: return launch<P, REGS, MAXT>(pl, b, n, m, xyz, pitch, idxs, new_xyz, xyz_copy, prof, s)
     if (pl.threads <= 256) {
         switch (pl.ppt) {
             PN2_FPS_CASE(2, true, 256); PN2_FPS_CASE(4, true, 256); PN2_FPS_CASE(6, true, 256);
@@ -471,10 +473,10 @@ using namespace pn2;
 
 extern "C" size_t pn2_furthest_point_sampling_workspace_bytes(int, int, int) { return 0; }
 
-static int fps_entry(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz, long long *prof,
-                     pn2_stream_t stream)
+static int fps_entry(int b, int n, int m, const float *xyz, int pitch, int *idxs, float *new_xyz, float *xyz_copy,
+                     long long *prof, pn2_stream_t stream)
 {
-    if (b < 0 || n < 0 || m < 0) return PN2_ERR_INVALID_ARGUMENT;
+    if (b < 0 || n < 0 || m < 0 || pitch < 3) return PN2_ERR_INVALID_ARGUMENT;
     if (b == 0 || m == 0) return PN2_OK;
     if (!idxs) return PN2_ERR_INVALID_ARGUMENT;
     if (n == 0) {
@@ -487,13 +489,21 @@ static int fps_entry(int b, int n, int m, const float *xyz, int *idxs, float *ne
     if (!xyz) return PN2_ERR_INVALID_ARGUMENT;
     FpsPlan pl;
     if (!make_plan(n, &pl)) return PN2_ERR_INVALID_ARGUMENT;   // n > 16 CTAs x 512 threads x 32 slots
-    return dispatch(pl, b, n, m, xyz, idxs, new_xyz, prof, as_stream(stream));
+    return dispatch(pl, b, n, m, xyz, pitch, idxs, new_xyz, xyz_copy, prof, as_stream(stream));
 }
 
 extern "C" int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *idxs,
                                                float *new_xyz, pn2_stream_t stream)
 {
-    return fps_entry(b, n, m, xyz, idxs, new_xyz, nullptr, stream);
+    return fps_entry(b, n, m, xyz, 3, idxs, new_xyz, nullptr, nullptr, stream);
+}
+
+// Same over rows of `pitch` floats whose first three are x, y, z (point_clouds read in place); xyz_copy (b,n,3), when
+// given, receives the contiguous coordinates the later kernels of the step read (written once while the points load).
+extern "C" int pn2_furthest_point_sampling_rows(int b, int n, int m, const float *rows, int pitch, int *idxs,
+                                                float *new_xyz, float *xyz_copy, pn2_stream_t stream)
+{
+    return fps_entry(b, n, m, rows, pitch, idxs, new_xyz, xyz_copy, nullptr, stream);
 }
 
 // Diagnostic: same launch, and prof[0..4] (device, 5 x int64) receives the SM cycles thread 0 of CTA 0
@@ -502,7 +512,7 @@ extern "C" int pn2_debug_fps_profile(int b, int n, int m, const float *xyz, int 
                                      pn2_stream_t stream)
 {
     if (!prof) return PN2_ERR_INVALID_ARGUMENT;
-    return fps_entry(b, n, m, xyz, idxs, nullptr, prof, stream);
+    return fps_entry(b, n, m, xyz, 3, idxs, nullptr, nullptr, prof, stream);
 }
 
 extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, void *, size_t,

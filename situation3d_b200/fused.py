@@ -217,6 +217,15 @@ def fps_into(xyz, inds, new_xyz):
                                                   stream_ptr()), "furthest_point_sampling_xyz")
 
 
+def fps_rows_into(rows, inds, new_xyz, xyz_copy):
+    """Sampling straight from (B, N, pitch) rows whose first three floats are xyz (``point_clouds`` in place); also
+    fills ``xyz_copy`` (B, N, 3), the contiguous coordinates the later kernels read."""
+    B, N, pitch = rows.shape
+    with torch.cuda.device(rows.device):
+        check(lib.pn2_furthest_point_sampling_rows(B, N, inds.shape[1], ptr(rows), pitch, ptr(inds), ptr(new_xyz),
+                                                   ptr(xyz_copy), stream_ptr()), "furthest_point_sampling_rows")
+
+
 def ball_query(xyz, new_xyz, radius, nsample, out=None):
     """Ball query (uniform grid for large scenes, plain scan otherwise); the workspace comes from
     PyTorch's caching allocator."""
