@@ -253,6 +253,27 @@ int pn2_token_gather(int b, int t, int c, const int *offsets, const int *sampled
                      const int *pooled_coords, float half_x, float half_y, float voxel_size, float *tokens,
                      float *positions, pn2_stream_t stream);
 
+/* ---- positional embedding looked up by integer voxel coordinate (csrc/voxel_pe.cu) ----
+ * Replaces the per-sample CPU loop of 3D-LLM's Blip2T5.forward / predict_answers
+ * (3DLLM_BLIP2-base/lavis/models/blip2_models/blip2_t5.py:104-118, :279-293) and Blip2OPT.forward
+ * (blip2_opt.py:92-104): pe[s,j, a*seg + k] = table[coords[s,j,a], k] for the axes a = 0,1,2 (channels
+ * 3*seg .. c-1 stay zero; the reference has seg = 469 = 1408 // 3, c = 1408, a (256, 469) table), then
+ *   PN2_VOXEL_PE_ADD: out (b,p,c)  = feat + scale * pe, the product rounded first as torch does (blip2_t5.py:118);
+ *   PN2_VOXEL_PE_CAT: out (b,2p,c) = cat([feat, pe], 1) (blip2_opt.py:104); feat may be NULL when rows [0,p) of
+ *                     every sample already hold the features -- then only the pe rows are written.
+ * coords: (b,p,coord_stride >= 3) device array of kind PN2_COORD_*; F32 is truncated toward zero like `.long()`
+ * (:107).  Indexing follows torch: a negative index counts from the end of the table; anything outside
+ * [-table_rows, table_rows) is an IndexError in the reference -- here *status (device int) becomes 1, the row is
+ * clamped, and the caller decides when to read the flag.  table (table_rows, seg) f32, feat/out f32 contiguous. */
+#define PN2_VOXEL_PE_ADD 0
+#define PN2_VOXEL_PE_CAT 1
+#define PN2_COORD_I32 0
+#define PN2_COORD_I64 1
+#define PN2_COORD_F32 2
+int pn2_voxel_pe(int b, int p, int c, int seg, int table_rows, int coord_kind, int coord_stride, const void *coords,
+                 const float *table, const float *feat, float *out, float scale, int mode, int *status,
+                 pn2_stream_t stream);
+
 /* ---- SM partitions for callers that keep several batches in flight (csrc/sm_partition.cu) ----------
  * The sampling chain of a batch is a latency-bound kernel of half-SM CTAs that lives ~2 ms; the fused MLP
  * kernels are persistent whole-SM CTAs.  pn2_sm_partition_create splits the current device's SMs into a first

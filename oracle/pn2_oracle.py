@@ -329,3 +329,47 @@ def column_tokens(coords_list, feats_list, tensor_stride, num_points=256, voxel_
         scene_positions.append(positions.unsqueeze(0))
         uniq.append(unique_coords); red.append(reduced_feats); inv.append(indices)
     return torch.cat(scene_feat, dim=0), torch.cat(scene_positions, dim=0), uniq, red, inv
+
+
+# ---- voxel-coordinate positional embedding before the Q-Former ---------
+def voxel_pe_table(rows=256, channels=1408 // 3, layout="concat"):
+    """PositionalEncoding1D(channels) evaluated on zeros(1, rows, channels) and squeezed
+    (3DLLM_BLIP2-base/lavis/models/blip2_models/blip2_t5.py:93-95).  The class comes from the third-party package
+    ``positional_encodings`` (imported at blip2_t5.py:11; not vendored, no version pinned anywhere in the
+    reference) -- PARITY UNPINNED for this function: it restates the package's published algorithm in float64 for
+    both published row layouts (``cat(sin, cos)`` up to 5.x, interleaved sin/cos from 6.0) and is compared by
+    tolerance only.  The gather/add below does not depend on it (the table is an input)."""
+    ch = (channels + 1) // 2 * 2
+    inv_freq = 1.0 / (10000.0 ** (np.arange(0, ch, 2, dtype=np.float64) / ch))
+    ang = np.arange(rows, dtype=np.float64)[:, None] * inv_freq[None, :]
+    if layout == "concat":
+        emb = np.concatenate([np.sin(ang), np.cos(ang)], axis=-1)
+    else:
+        emb = np.stack([np.sin(ang), np.cos(ang)], axis=-1).reshape(rows, ch)
+    return emb[:, :channels]
+
+
+def voxel_pe_all_pcs(pc, table, channels):
+    """blip2_t5.py:107-116 / blip2_opt.py:94-102 in numpy: per sample, the table rows of the x, y and z coordinate
+    side by side in the first 3*S channels of a zero (P, channels) array.  ``pc`` is truncated toward zero first
+    (``.long()``, :107); negative indices wrap and out-of-range ones raise IndexError, as torch's indexing does."""
+    pc = np.trunc(np.asarray(pc, dtype=np.float64)).astype(np.int64) if np.asarray(pc).dtype.kind == "f" else np.asarray(pc, dtype=np.int64)
+    table = np.asarray(table, dtype=np.float32)
+    R, S = table.shape
+    if ((pc[..., :3] < -R) | (pc[..., :3] >= R)).any():
+        raise IndexError("index out of range for a table of %d rows" % R)
+    B, P = pc.shape[:2]
+    all_pcs = np.zeros((B, P, channels), dtype=np.float32)
+    for j in range(B):
+        all_pcs[j, :, :3 * S] = np.concatenate([table[pc[j, :, i]] for i in range(3)], axis=-1)
+    return all_pcs
+
+
+def voxel_pe(pc_feat, pc, table, mode="add", scale=0.01):
+    """mode "add": pc_feat + 0.01 * all_pcs with the product rounded to fp32 first (blip2_t5.py:118);
+    mode "cat": cat([pc_feat, all_pcs], 1) (blip2_opt.py:104)."""
+    pc_feat = np.asarray(pc_feat, dtype=np.float32)
+    all_pcs = voxel_pe_all_pcs(pc, table, pc_feat.shape[-1])
+    if mode == "add":
+        return pc_feat + np.float32(scale) * all_pcs
+    return np.concatenate([pc_feat, all_pcs], axis=1)

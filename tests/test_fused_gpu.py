@@ -487,3 +487,61 @@ def test_backbone_pipeline_from_host_buffers():
             for k in want[j]:
                 assert torch.equal(got[k], want[j][k]), (j, k)
         pipe.drain()
+
+
+@pytest.mark.parametrize("name", ["rand", "sin"])
+def test_voxel_pe_vs_reference_statements(name):
+    """csrc/voxel_pe.cu against the outputs of the reference's own statements (blip2_t5.py:107-118 and
+    blip2_opt.py:93-104, executed unmodified by tests/golden/make_ref_voxel_pe_goldens.py): bit for bit in both
+    modes, for float coordinates (the reference's `.long()` done in the kernel) and for int64 / int32 ones."""
+    import os
+    from situation3d_b200.voxel_pe import voxel_pe
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_voxel_pe.npz"))
+    feat, pc, table = (torch.from_numpy(g[name + k]).cuda() for k in ("_pc_feat", "_pc", "_table"))
+    want_add, all_pcs = torch.from_numpy(g[name + "_add"]), torch.from_numpy(g[name + "_all_pcs"])
+    for coords in (pc, pc.long(), pc.int()):
+        assert torch.equal(voxel_pe(feat, coords, table, "add").cpu(), want_add)
+        cat = voxel_pe(feat, coords, table, "cat").cpu()
+        assert torch.equal(cat[:, :feat.shape[1]], feat.cpu()) and torch.equal(cat[:, feat.shape[1]:], all_pcs)
+    # in place, and a wider coordinate row (only the first three columns are read)
+    wide = torch.cat([pc, torch.full_like(pc[..., :1], 1e9)], dim=-1)
+    buf = feat.clone()
+    assert voxel_pe(buf, wide, table, "add", out=buf) is buf and torch.equal(buf.cpu(), want_add)
+
+
+@pytest.mark.parametrize("B,P,C,S,R", [(2, 5000, 1408, 469, 256), (1, 37, 30, 7, 5), (2, 33, 32, 9, 11), (3, 1, 1407, 469, 256), (1, 300, 1409, 469, 16)])
+def test_voxel_pe_vs_oracle(B, P, C, S, R):
+    """Reference-size batch and ragged shapes (C not a multiple of 4 takes the scalar path) against the numpy oracle."""
+    from situation3d_b200.voxel_pe import voxel_pe
+    g = torch.Generator().manual_seed(B * 1000 + P)
+    feat = torch.randn(B, P, C, generator=g)
+    pc = torch.randint(-R, R, (B, P, 3), generator=g)
+    table = torch.randn(R, S, generator=g)
+    for mode in ("add", "cat"):
+        got = voxel_pe(feat.cuda(), pc.cuda(), table.cuda(), mode).cpu().numpy()
+        assert np.array_equal(got, orc.voxel_pe(feat.numpy(), pc.numpy(), table.numpy(), mode)), mode
+
+
+def test_voxel_pe_module_and_errors():
+    from situation3d_b200.voxel_pe import VoxelPositionalEmbedding, sinusoid_table, voxel_pe
+    m = VoxelPositionalEmbedding().cuda()
+    assert m.pos_embedding.shape == (256, 469) and m.pos_embedding.is_cuda and len(m.state_dict()) == 0
+    feat = torch.randn(2, 64, 1408, device="cuda")
+    pc = torch.randint(0, 256, (2, 64, 3), device="cuda").float()
+    out = m(feat, pc)
+    want = orc.voxel_pe(feat.cpu().numpy(), pc.cpu().numpy(), sinusoid_table().numpy())
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert torch.equal(out[..., 1407], feat[..., 1407])                      # the 1408th channel gets no embedding
+    assert m(feat, pc, mode="cat").shape == (2, 128, 1408)
+    assert voxel_pe(feat[:0], pc[:0], m.pos_embedding).shape == (0, 64, 1408)
+    for bad in (256.0, -257.0, float("nan"), float("inf")):
+        pc2 = pc.clone()
+        pc2[1, 63, 2] = bad
+        with pytest.raises(IndexError):
+            m(feat, pc2)
+    _, status = voxel_pe(feat, pc, m.pos_embedding, validate=False)
+    assert int(status.item()) == 0
+    with pytest.raises(RuntimeError):
+        voxel_pe(feat.cpu(), pc.cpu(), m.pos_embedding.cpu())                  # no CPU path
+    with pytest.raises(RuntimeError):
+        voxel_pe(feat[..., :1000].contiguous(), pc, m.pos_embedding)            # 3 * 469 channels do not fit

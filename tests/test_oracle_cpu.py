@@ -249,3 +249,36 @@ def test_column_tokens_oracle_vs_reference_loop(name):
         cnt = torch.bincount(iv, minlength=u.shape[0]).float()
         want = torch.zeros_like(r).index_add_(0, iv, f) / (cnt + 1)[:, None]
         torch.testing.assert_close(r, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["rand", "sin"])
+def test_voxel_pe_oracle_vs_reference_statements(name):
+    """The oracle's restatement of blip2_t5.py:107-118 / blip2_opt.py:93-104 against the outputs of the reference's
+    own statements (executed unmodified by tests/golden/make_ref_voxel_pe_goldens.py): bit for bit, float
+    coordinates truncated toward zero and negative indices wrapped as torch does."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_voxel_pe.npz"))
+    feat, pc, table = g[name + "_pc_feat"], g[name + "_pc"], g[name + "_table"]
+    assert np.array_equal(orc.voxel_pe_all_pcs(pc, table, 1408), g[name + "_all_pcs"])
+    assert np.array_equal(orc.voxel_pe(feat, pc, table, "add"), g[name + "_add"])
+    cat = orc.voxel_pe(feat, pc, table, "cat")
+    assert np.array_equal(cat[:, :feat.shape[1]], feat) and np.array_equal(cat[:, feat.shape[1]:], g[name + "_all_pcs"])
+    assert (g[name + "_all_pcs"][..., 1407] == 0).all()                    # 1408 = 3 * 469 + 1: the last channel stays zero
+    with pytest.raises(IndexError):
+        orc.voxel_pe(feat, np.full_like(pc, table.shape[0]), table)
+
+
+@pytest.mark.parametrize("layout", ["concat", "interleave"])
+def test_voxel_pe_table(layout):
+    """The product's table builder (torch fp32, the package's operation order) against the oracle's float64
+    restatement of positional_encodings.PositionalEncoding1D -- tolerance only: the package is not in the reference
+    tree and its version is not pinned (parity unpinned for the table; it is an input of the kernel)."""
+    from situation3d_b200.voxel_pe import sinusoid_table
+    t = sinusoid_table(256, 469, layout)
+    assert t.shape == (256, 469) and t.dtype == torch.float32
+    # fp32 angles up to 255 rad carry ~1.5e-5 absolute error into sin / cos
+    np.testing.assert_allclose(t.numpy(), orc.voxel_pe_table(256, 469, layout), rtol=0, atol=5e-5)
+    if layout == "concat":
+        assert torch.all(t[0, :235] == 0) and torch.all(t[0, 235:] == 1)      # sin(0) block, then cos(0); column 469 is cut
+    else:
+        assert torch.all(t[0, 0::2] == 0) and torch.all(t[0, 1::2] == 1)
