@@ -274,6 +274,38 @@ int pn2_voxel_pe(int b, int p, int c, int seg, int table_rows, int coord_kind, i
                  const float *table, const float *feat, float *out, float scale, int mode, int *status,
                  pn2_stream_t stream);
 
+/* ---- point <-> pixel correspondences and back-projection of image features (csrc/projection.cu)
+ * Replaces ProjectionHelper.compute_projection / project of lib/projection.py (:191-254, :257-279) for all camera
+ * views of a scene at once.  Host arrays: intrinsic4 = {intrinsic[0][0], [1][1], [0][2], [1][2]}, depth_range3 =
+ * {depth_min, depth_max, accuracy}, corner_points (8,3) = ProjectionHelper._compute_corner_points (:29-46);
+ * width / height = image_dims[0] / [1].  Device arrays: points (n,3) f32, depth (views, height, width) f32,
+ * camera_to_world / world_to_camera (views,4,4) f32 row-major (the reference calls torch.inverse, :203; the caller
+ * supplies the inverse here).
+ * pn2_frustum_planes: corners (views,8,4) = compute_frustum_corners (:48-70), normals (views,6,3) =
+ *   compute_frustum_normals (:72-119); either may be NULL.
+ * pn2_compute_projection: per view v, indices_3d[v] / indices_2d[v] are the reference's (n+1) int64 arrays --
+ *   element 0 the number of correspondences, then the point indices in ascending order / their pixel indices
+ *   y * width + x, zero-padded (:246-252).  A view for which the reference returns None (:217,232,241) has count 0.
+ *   counts (views) i32 may be NULL.  A point corresponds to a pixel iff it passes the six half-space tests
+ *   round(dot * 100) / 100 < 0 (:143-146), projects to a pixel inside the image (:226-231) and the depth map agrees:
+ *   depth_min <= d <= depth_max and |d - z_camera| <= accuracy (:239-240).
+ * pn2_project: out (views, c, n) f32 = zeros; out[v, :, indices_3d[v][1+k]] = label[v, :, indices_2d[v][1+k]]
+ *   (:271-277); label (views, c, hw).  An index outside [0,n) / [0,hw) is an error in the reference: *status = 1.
+ * Workspaces are device memory owned by the caller (pn2_*_workspace_bytes). */
+int pn2_frustum_planes(int views, const float *camera_to_world, const float *intrinsic4, const float *depth_range3,
+                       int width, int height, const float *corner_points, float *corners, float *normals,
+                       pn2_stream_t stream);
+size_t pn2_compute_projection_workspace_bytes(int views, int n);
+int pn2_compute_projection(int views, int n, const float *points, const float *depth, const float *camera_to_world,
+                           const float *world_to_camera, const float *intrinsic4, const float *depth_range3,
+                           int width, int height, const float *corner_points, long long *indices_3d,
+                           long long *indices_2d, int *counts, void *workspace, size_t workspace_bytes,
+                           pn2_stream_t stream);
+size_t pn2_project_workspace_bytes(int views, int n);
+int pn2_project(int views, int c, int hw, int n, const float *label, const long long *indices_3d,
+                const long long *indices_2d, float *out, int *status, void *workspace, size_t workspace_bytes,
+                pn2_stream_t stream);
+
 /* ---- SM partitions for callers that keep several batches in flight (csrc/sm_partition.cu) ----------
  * The sampling chain of a batch is a latency-bound kernel of half-SM CTAs that lives ~2 ms; the fused MLP
  * kernels are persistent whole-SM CTAs.  pn2_sm_partition_create splits the current device's SMs into a first

@@ -295,3 +295,86 @@ PN2O_API void pn2o_group_points_grad(int b, int c, int n, int npoints, int nsamp
         }
     }
 }
+
+/* ---- point <-> pixel correspondences -----------------------------------------------
+ * lib/projection.py, ProjectionHelper.  The reference evaluates its 3- and 4-term dot products with torch.mm /
+ * torch.bmm (summation order left to the BLAS); this restatement fixes them as fmaf chains in index order and
+ * keeps every element-wise step separately rounded, which is also what csrc/projection.cu computes.  Pinned
+ * against the reference's own class run on the CPU (tests/golden/make_ref_projection_goldens.py): index lists
+ * identical on the golden scenes, corner / normal values to fp32 rounding. */
+
+/* compute_frustum_corners (:48-70) and compute_frustum_normals (:72-119).
+ * corner_points (8,3): _compute_corner_points (:29-46), w = 1.  corners (8,4), normals (6,3). */
+PN2O_API void pn2o_frustum_planes(const float *c2w, const float *corner_points, float *corners, float *normals)
+{
+    for (int k = 0; k < 8; ++k)
+        for (int r = 0; r < 4; ++r) {
+            float acc = c2w[r * 4 + 0] * corner_points[k * 3 + 0];
+            acc = fmaf(c2w[r * 4 + 1], corner_points[k * 3 + 1], acc);
+            acc = fmaf(c2w[r * 4 + 2], corner_points[k * 3 + 2], acc);
+            acc = fmaf(c2w[r * 4 + 3], 1.0f, acc);
+            corners[k * 4 + r] = acc;
+        }
+    /* plane k: origin corner, end of plane_vec1, end of plane_vec2 (front, right, roof, left, bottom, back) */
+    static const int tri[6][3] = {{0, 3, 1}, {1, 2, 5}, {2, 3, 6}, {3, 0, 7}, {0, 1, 4}, {5, 6, 4}};
+    for (int k = 0; k < 6; ++k) {
+        float a[3], b[3];
+        for (int j = 0; j < 3; ++j) {
+            a[j] = corners[tri[k][1] * 4 + j] - corners[tri[k][0] * 4 + j];
+            b[j] = corners[tri[k][2] * 4 + j] - corners[tri[k][0] * 4 + j];
+        }
+        const float p0 = a[1] * b[2], q0 = a[2] * b[1], p1 = a[2] * b[0], q1 = a[0] * b[2], p2 = a[0] * b[1], q2 = a[1] * b[0];
+        normals[k * 3 + 0] = p0 - q0;
+        normals[k * 3 + 1] = p1 - q1;
+        normals[k * 3 + 2] = p2 - q2;
+    }
+}
+
+/* compute_projection (:191-254) for one view.  intr4 = {fx, fy, cx, cy}, range3 = {depth_min, depth_max, accuracy}.
+ * idx3d / idx2d: (n+1) int64, element 0 = count; returns the count (0 where the reference returns None). */
+PN2O_API long long pn2o_compute_projection(int n, const float *points, const float *depth, const float *c2w,
+                                           const float *w2c, const float *intr4, const float *range3, int width,
+                                           int height, const float *corner_points, long long *idx3d, long long *idx2d)
+{
+    float corners[32], normals[18];
+    pn2o_frustum_planes(c2w, corner_points, corners, normals);
+    memset(idx3d, 0, sizeof(long long) * ((size_t)n + 1));
+    memset(idx2d, 0, sizeof(long long) * ((size_t)n + 1));
+    long long cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        const float x = points[(size_t)i * 3], y = points[(size_t)i * 3 + 1], z = points[(size_t)i * 3 + 2];
+        /* points_in_frustum (:139-150): planes 0-2 measured from corner 2, planes 3-5 from corner 4 */
+        int in = 1;
+        for (int k = 0; k < 6; ++k) {
+            const float *o = corners + (k < 3 ? 2 : 4) * 4;
+            const float px = x - o[0], py = y - o[1], pz = z - o[2];
+            const float d = fmaf(pz, normals[k * 3 + 2], fmaf(py, normals[k * 3 + 1], px * normals[k * 3 + 0]));
+            const float r = rintf(d * 100.0f);                 /* torch.round: half to even */
+            if (!(r < 0.0f)) in = 0;                            /* round(..) / 100 < 0 */
+        }
+        if (!in) continue;
+        /* world -> camera (:223) */
+        float cam[3];
+        for (int r = 0; r < 3; ++r) {
+            float acc = w2c[r * 4 + 0] * x;
+            acc = fmaf(w2c[r * 4 + 1], y, acc);
+            acc = fmaf(w2c[r * 4 + 2], z, acc);
+            cam[r] = fmaf(w2c[r * 4 + 3], 1.0f, acc);
+        }
+        /* camera -> image, rounded to a pixel (:226-228) */
+        const float mu = cam[0] * intr4[0], mv = cam[1] * intr4[1];
+        const float du = mu / cam[2], dv = mv / cam[2];
+        const float u = rintf(du + intr4[2]), v = rintf(dv + intr4[3]);
+        if (!(u >= 0.0f && v >= 0.0f && u < (float)width && v < (float)height)) continue;      /* :231 */
+        const long long pix = (long long)v * width + (long long)u;                               /* :236 */
+        const float dval = depth[pix];
+        const float diff = dval - cam[2];
+        if (!(dval >= range3[0] && dval <= range3[1] && fabsf(diff) <= range3[2])) continue;     /* :239-240 */
+        idx3d[1 + cnt] = i;
+        idx2d[1 + cnt] = pix;
+        ++cnt;
+    }
+    idx3d[0] = cnt;
+    idx2d[0] = cnt;
+    return cnt;
+}

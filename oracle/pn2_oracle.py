@@ -373,3 +373,67 @@ def voxel_pe(pc_feat, pc, table, mode="add", scale=0.01):
     if mode == "add":
         return pc_feat + np.float32(scale) * all_pcs
     return np.concatenate([pc_feat, all_pcs], axis=1)
+
+
+# ---- point <-> pixel correspondences and back-projection ---------------
+def corner_points(intrinsic, depth_min, depth_max, image_dims):
+    """ProjectionHelper._compute_corner_points with depth_to_skeleton (lib/projection.py:17-21,29-46) -> (8,3) f32:
+    the image corners (0,0), (W-1,0), (W-1,H-1), (0,H-1) at depth_min, then at depth_max, in the camera frame.
+    Evaluated in fp32 tensor arithmetic as the reference does when `intrinsic` is a float tensor."""
+    intrinsic = torch.as_tensor(intrinsic, dtype=torch.float32)
+    out = torch.empty(8, 3)
+    k = 0
+    for depth in (depth_min, depth_max):
+        for ux, uy in ((0, 0), (image_dims[0] - 1, 0), (image_dims[0] - 1, image_dims[1] - 1), (0, image_dims[1] - 1)):
+            x = (ux - intrinsic[0][2]) / intrinsic[0][0]
+            y = (uy - intrinsic[1][2]) / intrinsic[1][1]
+            out[k] = torch.Tensor([depth * x, depth * y, depth])
+            k += 1
+    return out
+
+
+def _projection_args(intrinsic, depth_min, depth_max, image_dims, accuracy):
+    intrinsic = torch.as_tensor(intrinsic, dtype=torch.float32)
+    intr4 = torch.tensor([intrinsic[0][0], intrinsic[1][1], intrinsic[0][2], intrinsic[1][2]], dtype=torch.float32)
+    range3 = torch.tensor([depth_min, depth_max, accuracy], dtype=torch.float32)
+    return intr4, range3, _f32(corner_points(intrinsic, depth_min, depth_max, image_dims))
+
+
+def frustum_planes(camera_to_world, intrinsic, depth_min, depth_max, image_dims):
+    """compute_frustum_corners + compute_frustum_normals (lib/projection.py:48-119) -> ((8,4), (6,3))."""
+    c2w = _f32(camera_to_world)
+    cp = _f32(corner_points(intrinsic, depth_min, depth_max, image_dims))
+    corners, normals = torch.empty(8, 4), torch.empty(6, 3)
+    lib().pn2o_frustum_planes(_p(c2w), _p(cp), _p(corners), _p(normals))
+    return corners, normals
+
+
+def compute_projection(points, depth, camera_to_world, world_to_camera, intrinsic, depth_min, depth_max, image_dims, accuracy):
+    """ProjectionHelper.compute_projection (lib/projection.py:191-254) for one view: (indices_3d, indices_2d), both
+    (num_points + 1,) int64 with the count first, or None where the reference returns None.  ``world_to_camera`` is
+    the caller's ``torch.inverse(camera_to_world)`` (:203)."""
+    points, depth = _f32(points), _f32(depth)
+    c2w, w2c = _f32(camera_to_world), _f32(world_to_camera)
+    intr4, range3, cp = _projection_args(intrinsic, depth_min, depth_max, image_dims, accuracy)
+    n = points.shape[0]
+    assert depth.numel() == image_dims[0] * image_dims[1]
+    i3 = torch.empty(n + 1, dtype=torch.int64)
+    i2 = torch.empty(n + 1, dtype=torch.int64)
+    fn = lib().pn2o_compute_projection
+    fn.restype = ctypes.c_longlong
+    cnt = fn(ctypes.c_int(n), _p(points), _p(depth), _p(c2w), _p(w2c), _p(intr4), _p(range3), ctypes.c_int(image_dims[0]),
+             ctypes.c_int(image_dims[1]), _p(cp), _p(i3), _p(i2))
+    return None if cnt == 0 else (i3, i2)
+
+
+def project(label, lin_indices_3d, lin_indices_2d, num_points):
+    """ProjectionHelper.project (lib/projection.py:257-279) in numpy: (C, num_points) zeros with the listed points
+    filled from the listed pixels."""
+    label = np.asarray(label, dtype=np.float32)
+    c = 1 if label.ndim == 2 else label.shape[0]
+    i3, i2 = np.asarray(lin_indices_3d), np.asarray(lin_indices_2d)
+    out = np.zeros((c, num_points), dtype=np.float32)
+    k = int(i3[0])
+    if k > 0:
+        out[:, i3[1:1 + k]] = label.reshape(c, -1)[:, i2[1:1 + k]]
+    return out

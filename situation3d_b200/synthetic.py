@@ -83,3 +83,50 @@ def randomize_bn_stats(module, seed=0):
                 m.weight.copy_(1.0 + 0.1 * torch.randn(m.num_features, generator=g))
                 m.bias.copy_(0.1 * torch.randn(m.num_features, generator=g))
     return module
+
+
+# ---- camera views of a scene, for the correspondence / back-projection path (projection.py) ---------------
+def look_at(eye, target):
+    """camera_to_world (4,4) float32 of a pinhole camera (x right, y down, z forward) at `eye` looking at `target`."""
+    eye, target = np.asarray(eye, dtype=np.float64), np.asarray(target, dtype=np.float64)
+    f = target - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(f, [0.0, 0.0, 1.0])
+    r /= np.linalg.norm(r)
+    d = np.cross(f, r)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = r, d, f, eye
+    return m.astype(np.float32)
+
+
+def make_views(points, n_views, seed=0, image_dims=(41, 32), focal=(37.01983, 38.52470), centre=(20.0, 15.5),
+               noise=0.02, holes=0.08):
+    """Random camera poses inside the scene's bounding box and, per view, a depth map that is a z-buffer of the
+    cloud itself (float64), with Gaussian noise and dropped pixels -- so that every stage of compute_projection
+    rejects some points.  Returns (intrinsic (4,4), poses (V,4,4), depths (V,H,W)), float32 numpy."""
+    rng = np.random.default_rng(seed)
+    pts = np.asarray(points, dtype=np.float64)[:, :3]
+    lo, hi = pts.min(0), pts.max(0)
+    lo, hi = np.where(hi - lo < 1.0, lo - 0.5, lo), np.where(hi - lo < 1.0, hi + 0.5, hi)     # degenerate clouds
+    W, H = image_dims
+    intrinsic = np.eye(4, dtype=np.float32)
+    intrinsic[0, 0], intrinsic[1, 1], intrinsic[0, 2], intrinsic[1, 2] = focal[0], focal[1], centre[0], centre[1]
+    hom = np.concatenate([pts, np.ones((pts.shape[0], 1))], 1).T
+    poses, depths = [], []
+    for _ in range(n_views):
+        eye = lo + (hi - lo) * rng.uniform(0.25, 0.75, 3)
+        target = lo + (hi - lo) * rng.uniform(0.0, 1.0, 3)
+        c2w = look_at(eye, target)
+        cam = np.linalg.inv(c2w.astype(np.float64)) @ hom
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = np.rint(cam[0] * float(intrinsic[0, 0]) / cam[2] + float(intrinsic[0, 2]))
+            v = np.rint(cam[1] * float(intrinsic[1, 1]) / cam[2] + float(intrinsic[1, 2]))
+        ok = (cam[2] > 0.05) & (u >= 0) & (v >= 0) & (u < W) & (v < H)
+        depth = np.full(W * H, np.inf)
+        np.minimum.at(depth, (v[ok] * W + u[ok]).astype(np.int64), cam[2][ok])
+        depth[~np.isfinite(depth)] = 0.0
+        depth = depth + rng.normal(0.0, noise, depth.shape) * (depth > 0)
+        depth[rng.uniform(size=depth.shape) < holes] = 0.0
+        poses.append(c2w)
+        depths.append(depth.reshape(H, W).astype(np.float32))
+    return intrinsic, np.stack(poses), np.stack(depths)

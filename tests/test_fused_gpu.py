@@ -545,3 +545,99 @@ def test_voxel_pe_module_and_errors():
         voxel_pe(feat.cpu(), pc.cpu(), m.pos_embedding.cpu())                  # no CPU path
     with pytest.raises(RuntimeError):
         voxel_pe(feat[..., :1000].contiguous(), pc, m.pos_embedding)            # 3 * 469 channels do not fit
+
+
+def _projection_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_projection.npz"))
+
+
+def test_projection_vs_reference_class():
+    """csrc/projection.cu behind the reference's ProjectionHelper interface against the outputs of the reference's own
+    class (lib/projection.py run unmodified on the CPU by tests/golden/make_ref_projection_goldens.py): the index
+    lists of every view are identical (batched and one view at a time, `None` for the view that sees nothing),
+    project() is identical, corners / normals agree to fp32 rounding."""
+    from situation3d_b200.projection import ProjectionHelper
+    g = _projection_golden()
+    dmin, dmax, acc = (float(v) for v in g["params"])
+    helper = ProjectionHelper(torch.from_numpy(g["intrinsic"]), dmin, dmax, [int(v) for v in g["image_dims"]], acc)
+    assert np.array_equal(helper.corner_points[:, :3].cpu().numpy(), g["corner_points"]) and helper.corner_points.is_cuda
+    points = torch.from_numpy(g["points"]).cuda()
+    poses, depths = torch.from_numpy(g["poses"]).cuda(), torch.from_numpy(g["depths"]).cuda()
+    n, V = points.shape[0], poses.shape[0]
+    i3, i2, counts = helper.compute_projection_views(points, depths, poses)
+    assert i3.dtype == torch.int64 and i3.shape == (V, n + 1)
+    assert np.array_equal(i3.cpu().numpy(), g["indices_3d"].astype(np.int64))
+    assert np.array_equal(i2.cpu().numpy(), g["indices_2d"].astype(np.int64))
+    assert np.array_equal(counts.cpu().numpy(), g["indices_3d"][:, 0])
+    for v in range(V):
+        res = helper.compute_projection(points, depths[v], poses[v])
+        if g["indices_3d"][v, 0] == 0:
+            assert res is None
+        else:
+            assert np.array_equal(res[0].cpu().numpy(), g["indices_3d"][v]) and np.array_equal(res[1].cpu().numpy(), g["indices_2d"][v])
+        cc = helper.compute_frustum_corners(poses[v])
+        assert cc.shape == (8, 4, 1)
+        np.testing.assert_allclose(cc.squeeze(-1).cpu().numpy(), g["corners"][v], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(helper.compute_frustum_normals(cc).cpu().numpy(), g["normals"][v], rtol=1e-4, atol=1e-4)
+    label = torch.from_numpy(g["label"]).cuda()
+    out = helper.project(label[3], i3[3], i2[3], n)
+    assert out.shape == (label.shape[1], n) and np.array_equal(out.cpu().numpy(), g["project_view3"])
+    allv = helper.project_views(label, i3, i2, n)
+    assert torch.equal(allv[3], out)
+    np.testing.assert_allclose(allv.double().sum((1, 2)).cpu().numpy(), g["project_checksum"], rtol=1e-9, atol=1e-9)
+    one = helper.project(label[3, 0], i3[3], i2[3], n)                       # a single (H, W) plane -> (1, n)
+    assert one.shape == (1, n) and torch.equal(one[0], out[0])
+
+
+@pytest.mark.parametrize("n,V,C", [(50000, 24, 128), (4097, 3, 5), (1, 2, 1), (300, 1, 33)])
+def test_projection_vs_oracle(n, V, C):
+    """Scene-size clouds and ragged shapes (segment boundaries at 4096 points) against the C oracle, bit for bit;
+    then the properties the lists must have (ascending points, count first, zero padding) and the back-projection
+    against numpy."""
+    from situation3d_b200.projection import ProjectionHelper
+    from situation3d_b200.synthetic import make_scene, make_views
+    pts = make_scene(5, n_points=max(n, 64), n_features=1)[:n, :3].astype(np.float32)
+    intrinsic, poses, depths = make_views(pts, V, seed=n)
+    dims, dmin, dmax, acc = [41, 32], 0.4, 4.0, 0.05
+    helper = ProjectionHelper(torch.from_numpy(intrinsic), dmin, dmax, dims, acc)
+    points = torch.from_numpy(pts).cuda()
+    c2w = torch.from_numpy(poses).cuda()
+    w2c = torch.inverse(c2w)
+    i3, i2, counts = helper.compute_projection_views(points, torch.from_numpy(depths).cuda(), c2w, w2c)
+    i3h, i2h, w2ch = i3.cpu(), i2.cpu(), w2c.cpu()
+    total = 0
+    for v in range(V):
+        want = orc.compute_projection(torch.from_numpy(pts), torch.from_numpy(depths[v]), torch.from_numpy(poses[v]), w2ch[v],
+                                      torch.from_numpy(intrinsic), dmin, dmax, dims, acc)
+        k = int(i3h[v, 0])
+        if want is None:
+            assert k == 0 and int(i3h[v].abs().sum()) == 0 and int(i2h[v].abs().sum()) == 0
+            continue
+        assert torch.equal(i3h[v], want[0]) and torch.equal(i2h[v], want[1]), v
+        assert k == int(counts[v]) and bool((i3h[v, 2:1 + k] > i3h[v, 1:k]).all()) and int(i3h[v, 1 + k:].abs().sum()) == 0
+        total += k
+    if n >= 4097:
+        assert total > 0                                                       # the synthetic views do see the cloud
+    label = torch.randn(V, C, dims[1], dims[0], generator=torch.Generator().manual_seed(n))
+    got = helper.project_views(label.cuda(), i3, i2, n).cpu().numpy()
+    for v in range(V):
+        assert np.array_equal(got[v], orc.project(label[v].numpy(), i3h[v].numpy(), i2h[v].numpy(), n)), v
+
+
+def test_projection_errors():
+    from situation3d_b200.projection import ProjectionHelper
+    helper = ProjectionHelper(torch.eye(4), 0.4, 4.0, [41, 32], 0.05)
+    with pytest.raises(RuntimeError):
+        ProjectionHelper(torch.eye(4), 0.4, 4.0, [41, 32], 0.05, cuda=False)          # no CPU path
+    with pytest.raises(RuntimeError):
+        helper.compute_projection(torch.zeros(10, 3), torch.zeros(32, 41), torch.eye(4))
+    i3 = torch.zeros(11, dtype=torch.int64, device="cuda")
+    i2 = torch.zeros(11, dtype=torch.int64, device="cuda")
+    i3[0], i2[0], i3[1], i2[1] = 1, 1, 4, 32 * 41                                      # pixel index one past the image
+    with pytest.raises(IndexError):
+        helper.project(torch.zeros(2, 32, 41, device="cuda"), i3, i2, 10)
+    i2[1] = 5
+    lab = torch.arange(2 * 32 * 41, dtype=torch.float32, device="cuda").reshape(2, 32, 41)
+    out = helper.project(lab, i3, i2, 10)
+    assert out[:, 4].tolist() == [5.0, 5.0 + 32 * 41] and float(out.abs().sum()) == 10.0 + 32 * 41

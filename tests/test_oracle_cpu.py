@@ -282,3 +282,41 @@ def test_voxel_pe_table(layout):
         assert torch.all(t[0, :235] == 0) and torch.all(t[0, 235:] == 1)      # sin(0) block, then cos(0); column 469 is cut
     else:
         assert torch.all(t[0, 0::2] == 0) and torch.all(t[0, 1::2] == 1)
+
+
+def _projection_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_projection.npz"))
+
+
+def test_projection_oracle_vs_reference_class():
+    """oracle compute_projection / frustum planes / project against the reference's own ProjectionHelper run on the CPU
+    (tests/golden/make_ref_projection_goldens.py): index lists identical for every view (one view sees nothing ->
+    None), corners and normals to fp32 rounding (the reference's bmm / cross leave the summation order open)."""
+    g = _projection_golden()
+    intrinsic, (dmin, dmax, acc), dims = torch.from_numpy(g["intrinsic"]), [float(v) for v in g["params"]], [int(v) for v in g["image_dims"]]
+    np.testing.assert_allclose(orc.corner_points(intrinsic, dmin, dmax, dims).numpy(), g["corner_points"], rtol=0, atol=0)
+    points = torch.from_numpy(g["points"])
+    n = points.shape[0]
+    nviews = g["poses"].shape[0]
+    seen_none = False
+    for v in range(nviews):
+        c2w = torch.from_numpy(g["poses"][v])
+        res = orc.compute_projection(points, torch.from_numpy(g["depths"][v]), c2w, torch.inverse(c2w), intrinsic, dmin, dmax, dims, acc)
+        want3, want2 = g["indices_3d"][v].astype(np.int64), g["indices_2d"][v].astype(np.int64)
+        if want3[0] == 0:
+            assert res is None
+            seen_none = True
+            continue
+        assert np.array_equal(res[0].numpy(), want3) and np.array_equal(res[1].numpy(), want2)
+        k = int(want3[0])
+        assert (np.diff(want3[1:1 + k]) > 0).all() and (want3[1 + k:] == 0).all()           # ascending, zero-padded
+        corners, normals = orc.frustum_planes(c2w, intrinsic, dmin, dmax, dims)
+        np.testing.assert_allclose(corners.numpy(), g["corners"][v], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(normals.numpy(), g["normals"][v], rtol=1e-4, atol=1e-4)
+    assert seen_none
+    out = orc.project(g["label"][3], g["indices_3d"][3], g["indices_2d"][3], n)
+    assert np.array_equal(out, g["project_view3"])
+    for v in range(nviews):
+        s = orc.project(g["label"][v], g["indices_3d"][v], g["indices_2d"][v], n).astype(np.float64).sum()
+        assert abs(s - g["project_checksum"][v]) <= 1e-9 * max(1.0, abs(g["project_checksum"][v]))
