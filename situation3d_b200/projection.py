@@ -103,7 +103,8 @@ class ProjectionHelper:
         depth = depth.to(torch.float32).reshape(V, -1).contiguous()
         if points.dim() != 2 or points.shape[1] != 3 or depth.shape[1] != W * H:
             raise RuntimeError("ProjectionHelper: expected points (N,3) and depth (V,%d,%d)" % (H, W))
-        w2c = torch.inverse(c2w) if world_to_camera is None else world_to_camera.to(torch.float32).reshape(V, 4, 4).contiguous()   # :203
+        w2c = torch.inverse(c2w) if world_to_camera is None else world_to_camera.to(torch.float32).reshape(V, 4, 4)               # :203
+        w2c = w2c.contiguous()          # torch.inverse hands back column-major batches
         dev = points.device
         i3 = torch.empty((V, N + 1), dtype=torch.int64, device=dev)
         i2 = torch.empty((V, N + 1), dtype=torch.int64, device=dev)
