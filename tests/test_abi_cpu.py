@@ -184,3 +184,35 @@ def test_split_first_layer_rule():
     assert fused.split_first_layer(256, 128)       # SA3 / SA4: 272 -> 144
     assert not fused.split_first_layer(129, 96)    # widths the per-point GEMM does not cover
     assert not fused.split_first_layer(6, 64)
+
+
+REF_PROJECTION = "/root/reference/lib/projection.py"
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_PROJECTION), reason="reference tree not present")
+def test_projection_helper_signatures_match_reference():
+    """ProjectionHelper keeps the reference's constructor and method signatures (lib/projection.py:5-279); the batched
+    forms are additions."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_projection_sig", REF_PROJECTION)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from situation3d_b200.projection import ProjectionHelper
+
+    def params(fn):
+        return [(p.name, p.kind, p.default) for p in inspect.signature(fn).parameters.values()]
+
+    for name in ("__init__", "depth_to_skeleton", "skeleton_to_depth", "compute_frustum_corners", "compute_frustum_normals",
+                 "compute_projection", "project"):
+        assert params(getattr(ProjectionHelper, name)) == params(getattr(ref.ProjectionHelper, name)), name
+    assert hasattr(ProjectionHelper, "compute_projection_views") and hasattr(ProjectionHelper, "project_views")
+
+
+def test_voxel_pe_and_projection_reject_cpu_tensors():
+    """The widened rows have no CPU path either: host tensors raise instead of being computed somewhere else."""
+    from situation3d_b200.voxel_pe import voxel_pe
+    with pytest.raises(RuntimeError):
+        voxel_pe(torch.zeros(1, 2, 1408), torch.zeros(1, 2, 3), torch.zeros(4, 469))
+    from situation3d_b200.projection import ProjectionHelper
+    with pytest.raises(RuntimeError):
+        ProjectionHelper(torch.eye(4), 0.4, 4.0, [41, 32], 0.05, cuda=False)
