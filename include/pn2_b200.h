@@ -283,6 +283,8 @@ int pn2_voxel_pe(int b, int p, int c, int seg, int table_rows, int coord_kind, i
  * supplies the inverse here).
  * pn2_frustum_planes: corners (views,8,4) = compute_frustum_corners (:48-70), normals (views,6,3) =
  *   compute_frustum_normals (:72-119); either may be NULL.
+ * pn2_points_in_frustum: points_in_frustum (:121-155) for the caller's corners (8,4) / normals (6,3) (device):
+ *   mask (n) u8 (may be NULL) and *count (device int) = number of points inside.
  * pn2_compute_projection: per view v, indices_3d[v] / indices_2d[v] are the reference's (n+1) int64 arrays --
  *   element 0 the number of correspondences, then the point indices in ascending order / their pixel indices
  *   y * width + x, zero-padded (:246-252).  A view for which the reference returns None (:217,232,241) has count 0.
@@ -295,6 +297,8 @@ int pn2_voxel_pe(int b, int p, int c, int seg, int table_rows, int coord_kind, i
 int pn2_frustum_planes(int views, const float *camera_to_world, const float *intrinsic4, const float *depth_range3,
                        int width, int height, const float *corner_points, float *corners, float *normals,
                        pn2_stream_t stream);
+int pn2_points_in_frustum(int n, const float *points, const float *corners, const float *normals,
+                          unsigned char *mask, int *count, pn2_stream_t stream);
 size_t pn2_compute_projection_workspace_bytes(int views, int n);
 int pn2_compute_projection(int views, int n, const float *points, const float *depth, const float *camera_to_world,
                            const float *world_to_camera, const float *intrinsic4, const float *depth_range3,

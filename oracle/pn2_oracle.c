@@ -378,3 +378,24 @@ PN2O_API long long pn2o_compute_projection(int n, const float *points, const flo
     idx2d[0] = cnt;
     return cnt;
 }
+
+/* points_in_frustum (lib/projection.py:121-155) for given corners (8,4) and normals (6,3): mask (n) bytes, returns
+ * the number of points inside. */
+PN2O_API long long pn2o_points_in_frustum(int n, const float *points, const float *corners, const float *normals,
+                                          unsigned char *mask)
+{
+    long long cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        const float x = points[(size_t)i * 3], y = points[(size_t)i * 3 + 1], z = points[(size_t)i * 3 + 2];
+        int in = 1;
+        for (int k = 0; k < 6; ++k) {
+            const float *o = corners + (k < 3 ? 2 : 4) * 4;
+            const float px = x - o[0], py = y - o[1], pz = z - o[2];
+            const float d = fmaf(pz, normals[k * 3 + 2], fmaf(py, normals[k * 3 + 1], px * normals[k * 3 + 0]));
+            if (!(rintf(d * 100.0f) < 0.0f)) in = 0;
+        }
+        if (mask) mask[i] = (unsigned char)in;
+        cnt += in;
+    }
+    return cnt;
+}

@@ -437,3 +437,15 @@ def project(label, lin_indices_3d, lin_indices_2d, num_points):
     if k > 0:
         out[:, i3[1:1 + k]] = label.reshape(c, -1)[:, i2[1:1 + k]]
     return out
+
+
+def points_in_frustum(corner_coords, normals, new_pts, return_mask=False):
+    """ProjectionHelper.points_in_frustum (lib/projection.py:121-155): bool mask or the number of points inside."""
+    cc = _f32(torch.as_tensor(corner_coords, dtype=torch.float32).reshape(8, 4))
+    nr = _f32(torch.as_tensor(normals, dtype=torch.float32).reshape(6, 3))
+    pts = _f32(new_pts)
+    mask = torch.empty(pts.shape[0], dtype=torch.uint8)
+    fn = lib().pn2o_points_in_frustum
+    fn.restype = ctypes.c_longlong
+    cnt = fn(ctypes.c_int(pts.shape[0]), _p(pts), _p(cc), _p(nr), _p(mask))
+    return mask.bool() if return_mask else int(cnt)

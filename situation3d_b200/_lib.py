@@ -89,6 +89,7 @@ _PROTOTYPES = {
     "pn2_token_gather": (_i, [_i, _i, _i, _p, _p, _p, _p, _f, _f, _f, _p, _p, _p]),
     "pn2_voxel_pe": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _i, _p, _p]),
     "pn2_frustum_planes": (_i, [_i, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "pn2_points_in_frustum": (_i, [_i, _p, _p, _p, _p, _p, _p]),
     "pn2_compute_projection_workspace_bytes": (c_size_t, [_i, _i]),
     "pn2_compute_projection": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, c_size_t, _p]),
     "pn2_project_workspace_bytes": (c_size_t, [_i, _i]),

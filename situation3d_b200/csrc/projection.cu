@@ -70,9 +70,8 @@ __device__ __forceinline__ void frustum_planes(const float *__restrict__ m, cons
     for (int j = 0; j < 3; ++j) { pl.c2[j] = c[2][j]; pl.c4[j] = c[4][j]; }
 }
 
-// The pixel index y * width + x a point corresponds to in this view, or -1 (:214-240 as one predicate).
-__device__ __forceinline__ int project_point(float x, float y, float z, const ProjPlanes &pl, const float *__restrict__ w2c,
-                                             const float *__restrict__ depth, const ProjCamera &cam)
+// points_in_frustum (:121-155): planes 0-2 are measured from corner 2, planes 3-5 from corner 4.
+__device__ __forceinline__ bool point_in_frustum(float x, float y, float z, const ProjPlanes &pl)
 {
     const float ax = __fsub_rn(x, pl.c2[0]), ay = __fsub_rn(y, pl.c2[1]), az = __fsub_rn(z, pl.c2[2]);
     const float bx = __fsub_rn(x, pl.c4[0]), by = __fsub_rn(y, pl.c4[1]), bz = __fsub_rn(z, pl.c4[2]);
@@ -83,7 +82,14 @@ __device__ __forceinline__ int project_point(float x, float y, float z, const Pr
         const float d = __fmaf_rn(pz, pl.normal[k][2], __fmaf_rn(py, pl.normal[k][1], __fmul_rn(px, pl.normal[k][0])));
         in = in && (rintf(__fmul_rn(d, 100.0f)) < 0.0f);           // round(d * 100) / 100 < 0
     }
-    if (!in) return -1;
+    return in;
+}
+
+// The pixel index y * width + x a point corresponds to in this view, or -1 (:214-240 as one predicate).
+__device__ __forceinline__ int project_point(float x, float y, float z, const ProjPlanes &pl, const float *__restrict__ w2c,
+                                             const float *__restrict__ depth, const ProjCamera &cam)
+{
+    if (!point_in_frustum(x, y, z, pl)) return -1;
     float cam3[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -111,6 +117,25 @@ frustum_planes_kernel(int views, const float *__restrict__ c2w, ProjCamera cam, 
     if (normals)
         for (int k = 0; k < 6; ++k)
             for (int j = 0; j < 3; ++j) normals[(size_t)v * 18 + k * 3 + j] = pl.normal[k][j];
+}
+
+// points_in_frustum as the reference exposes it: the caller's corners (8,4) and normals (6,3), a byte mask and a count.
+__global__ void __launch_bounds__(kProjThreads)
+points_in_frustum_kernel(int n, const float *__restrict__ points, const float *__restrict__ corners, const float *__restrict__ normals,
+                         unsigned char *__restrict__ mask, int *__restrict__ count)
+{
+    __shared__ ProjPlanes pl;
+    if (threadIdx.x < 18) pl.normal[threadIdx.x / 3][threadIdx.x % 3] = normals[threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 35) { pl.c2[threadIdx.x - 32] = corners[2 * 4 + threadIdx.x - 32]; pl.c4[threadIdx.x - 32] = corners[4 * 4 + threadIdx.x - 32]; }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = blockIdx.x * kProjThreads + threadIdx.x; i < n; i += gridDim.x * kProjThreads) {
+        const bool in = point_in_frustum(points[(size_t)i * 3], points[(size_t)i * 3 + 1], points[(size_t)i * 3 + 2], pl);
+        if (mask) mask[i] = in ? 1 : 0;
+        cnt += in;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(count, cnt);
 }
 
 // Pass 1: pixel-or-minus-one per (view, point) and the number of correspondences per (view, segment).
@@ -265,6 +290,19 @@ extern "C" int pn2_frustum_planes(int views, const float *camera_to_world, const
     if (!camera_to_world) return PN2_ERR_INVALID_ARGUMENT;
     frustum_planes_kernel<<<ceil_div(views, 32), 32, 0, as_stream(stream)>>>(views, camera_to_world, cam, corners, normals);
     PN2_LAUNCH_CHECK("frustum_planes");
+    return PN2_OK;
+}
+
+extern "C" int pn2_points_in_frustum(int n, const float *points, const float *corners, const float *normals,
+                                     unsigned char *mask, int *count, pn2_stream_t stream)
+{
+    if (n < 0 || !count) return PN2_ERR_INVALID_ARGUMENT;
+    PN2_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), as_stream(stream)));
+    if (n == 0) return PN2_OK;
+    if (!points || !corners || !normals) return PN2_ERR_INVALID_ARGUMENT;
+    const int want = ceil_div(n, kProjThreads), cap = stream_sm_count(as_stream(stream)) * 8;
+    points_in_frustum_kernel<<<want < cap ? want : cap, kProjThreads, 0, as_stream(stream)>>>(n, points, corners, normals, mask, count);
+    PN2_LAUNCH_CHECK("points_in_frustum");
     return PN2_OK;
 }
 

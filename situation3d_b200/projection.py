@@ -20,6 +20,30 @@ def _host_floats(vals):
     return torch.tensor([float(v) for v in vals], dtype=torch.float32)
 
 
+@torch.no_grad()
+def project_views(label, lin_indices_3d, lin_indices_2d, num_points):
+    """label (V,C,H,W) or (V,C,HW); index lists (V,num_points+1) -> (V,C,num_points)."""
+    if not (label.is_cuda and lin_indices_3d.is_cuda and lin_indices_2d.is_cuda):
+        raise RuntimeError("ProjectionHelper: CUDA tensors required (there is no CPU path)")
+    V, C = label.shape[0], label.shape[1]
+    label = label.to(torch.float32).reshape(V, C, -1).contiguous()
+    i3 = lin_indices_3d.to(torch.int64).reshape(V, -1).contiguous()
+    i2 = lin_indices_2d.to(torch.int64).reshape(V, -1).contiguous()
+    if i3.shape[1] != num_points + 1 or i2.shape[1] != num_points + 1:
+        raise RuntimeError("ProjectionHelper.project: index lists must have num_points + 1 entries")
+    dev = label.device
+    out = torch.empty((V, C, num_points), dtype=torch.float32, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = lib.pn2_project_workspace_bytes(V, num_points)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.pn2_project(V, C, label.shape[2], num_points, ptr(label), ptr(i3), ptr(i2), ptr(out), ptr(status), ptr(ws),
+                              nbytes, stream_ptr()), "project")
+    if int(status.item()) != 0:
+        raise IndexError("ProjectionHelper.project: index out of range")
+    return out
+
+
 class ProjectionHelper:
     def __init__(self, intrinsic, depth_min, depth_max, image_dims, accuracy, cuda=True):
         if not cuda:
@@ -90,6 +114,22 @@ class ProjectionHelper:
                                          int(self.image_dims[1]), ptr(host), None, ptr(normals), stream_ptr()), "frustum_planes")
         return normals[0]
 
+    def points_in_frustum(self, corner_coords, normals, new_pts, return_mask=False):
+        """Boolean mask (``return_mask=True``) or number of ``new_pts`` (M,3) inside the frustum given by its corners
+        (8,4[,1]) and plane normals (6,3) (lib/projection.py:121-155)."""
+        if not (corner_coords.is_cuda and normals.is_cuda):
+            raise RuntimeError("ProjectionHelper: CUDA tensors required (there is no CPU path)")
+        dev = corner_coords.device
+        pts = new_pts.to(dev, torch.float32).contiguous()            # the reference moves new_pts to the GPU itself (:133)
+        cc = corner_coords.reshape(8, 4).to(torch.float32).contiguous()
+        nr = normals.reshape(6, 3).to(torch.float32).contiguous()
+        m = pts.shape[0]
+        mask = torch.empty(m, dtype=torch.uint8, device=dev) if return_mask else None
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pn2_points_in_frustum(m, ptr(pts), ptr(cc), ptr(nr), ptr(mask), ptr(count), stream_ptr()), "points_in_frustum")
+        return mask.bool() if return_mask else count[0].long()
+
     def compute_projection_views(self, points, depth, camera_to_world, world_to_camera=None):
         """All views of a scene at once.  points (N,3), depth (V,H,W), camera_to_world (V,4,4), all CUDA f32.
         Returns (indices_3d (V,N+1) int64, indices_2d (V,N+1) int64, counts (V,) int32) -- row v is what the
@@ -125,31 +165,27 @@ class ProjectionHelper:
             return None
         return i3[0], i2[0]
 
-    @torch.no_grad()
     def project_views(self, label, lin_indices_3d, lin_indices_2d, num_points):
         """label (V,C,H,W) or (V,C,HW); index lists (V,num_points+1) -> (V,C,num_points)."""
-        if not (label.is_cuda and lin_indices_3d.is_cuda and lin_indices_2d.is_cuda):
-            raise RuntimeError("ProjectionHelper: CUDA tensors required (there is no CPU path)")
-        V, C = label.shape[0], label.shape[1]
-        label = label.to(torch.float32).reshape(V, C, -1).contiguous()
-        i3 = lin_indices_3d.to(torch.int64).reshape(V, -1).contiguous()
-        i2 = lin_indices_2d.to(torch.int64).reshape(V, -1).contiguous()
-        if i3.shape[1] != num_points + 1 or i2.shape[1] != num_points + 1:
-            raise RuntimeError("ProjectionHelper.project: index lists must have num_points + 1 entries")
-        dev = label.device
-        out = torch.empty((V, C, num_points), dtype=torch.float32, device=dev)
-        status = torch.empty(1, dtype=torch.int32, device=dev)
-        nbytes = lib.pn2_project_workspace_bytes(V, num_points)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            check(lib.pn2_project(V, C, label.shape[2], num_points, ptr(label), ptr(i3), ptr(i2), ptr(out), ptr(status), ptr(ws),
-                                  nbytes, stream_ptr()), "project")
-        if int(status.item()) != 0:
-            raise IndexError("ProjectionHelper.project: index out of range")
-        return out
+        return project_views(label, lin_indices_3d, lin_indices_2d, num_points)
 
     @torch.no_grad()
     def project(self, label, lin_indices_3d, lin_indices_2d, num_points):
         """One view, the reference's signature (lib/projection.py:257-279): label (C,H,W) or (H,W) -> (C,num_points)."""
         c = 1 if label.dim() == 2 else label.shape[0]
         return self.project_views(label.reshape(1, c, -1), lin_indices_3d.reshape(1, -1), lin_indices_2d.reshape(1, -1), num_points)[0]
+
+
+class Projection(torch.autograd.Function):
+    """The reference's autograd wrapper of the back-projection (lib/projection.py:283-309).  forward is
+    ProjectionHelper.project.  The reference's backward cannot run (``save_for_backward`` is commented out at :296,
+    so ``ctx.saved_variables`` is empty, and the gradient shape is hard-wired to 32 x 41); it is not reproduced."""
+
+    @staticmethod
+    def forward(ctx, label, lin_indices_3d, lin_indices_2d, num_points):
+        c = 1 if label.dim() == 2 else label.shape[0]
+        return project_views(label.reshape(1, c, -1), lin_indices_3d.reshape(1, -1), lin_indices_2d.reshape(1, -1), num_points)[0]
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        raise NotImplementedError("Projection.backward: the reference's backward is unreachable (lib/projection.py:296)")

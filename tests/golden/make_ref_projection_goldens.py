@@ -6,7 +6,7 @@
 CPU -- ``Tensor.cuda()`` is the identity while it runs.  A synthetic room (points on the floor, the walls and a few
 boxes) is seen from several camera poses; each view's depth map is a z-buffer of the cloud itself with holes and
 noise, so that every stage of compute_projection (frustum, image range, depth range, depth agreement) rejects some
-points.  Stored: inputs, the reference's index lists, frustum corners / normals, and project() outputs.
+points.  Stored: inputs, the reference's index lists, frustum corners / normals / point masks, and project() outputs.
 """
 import importlib.util
 import os
@@ -89,7 +89,7 @@ def main():
     n = 6000
     points = room(g, n)
     views = 10
-    poses, depths, i3s, i2s, corners, normals = [], [], [], [], [], []
+    poses, depths, i3s, i2s, corners, normals, masks = [], [], [], [], [], [], []
     for v in range(views):
         eye = torch.tensor([float(torch.rand(1, generator=g) * 4 - 2), float(torch.rand(1, generator=g) * 3 - 1.5),
                             float(torch.rand(1, generator=g) * 1.2 + 0.8)])
@@ -106,6 +106,8 @@ def main():
             i3, i2 = res
         cc = helper.compute_frustum_corners(c2w)
         corners.append(cc.squeeze(-1)); normals.append(helper.compute_frustum_normals(cc))
+        masks.append(helper.points_in_frustum(cc, normals[-1], points, return_mask=True))
+        assert int(helper.points_in_frustum(cc, normals[-1], points)) == int(masks[-1].sum())
         poses.append(c2w); depths.append(depth); i3s.append(i3); i2s.append(i2)
         mine = orc.compute_projection(points, depth, c2w, torch.inverse(c2w), intrinsic, DEPTH_MIN, DEPTH_MAX, IMAGE_DIMS, ACCURACY)
         same = (mine is None and res is None) or (mine is not None and res is not None and torch.equal(mine[0], i3) and torch.equal(mine[1], i2))
@@ -115,7 +117,7 @@ def main():
     out.update({"points": points.numpy(), "poses": torch.stack(poses).numpy(), "depths": torch.stack(depths).numpy(),
                 "indices_3d": torch.stack(i3s).numpy().astype(np.int32), "indices_2d": torch.stack(i2s).numpy().astype(np.int32),
                 "corners": torch.stack(corners).numpy(), "normals": torch.stack(normals).numpy(),
-                "label": label.numpy(), "project_view3": proj[3].numpy(),
+                "label": label.numpy(), "frustum_masks": np.packbits(torch.stack(masks).numpy(), axis=1), "project_view3": proj[3].numpy(),
                 "project_checksum": proj.double().sum((1, 2)).numpy()})
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_projection.npz")
     np.savez_compressed(path, **out)

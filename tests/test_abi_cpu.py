@@ -203,9 +203,11 @@ def test_projection_helper_signatures_match_reference():
         return [(p.name, p.kind, p.default) for p in inspect.signature(fn).parameters.values()]
 
     for name in ("__init__", "depth_to_skeleton", "skeleton_to_depth", "compute_frustum_corners", "compute_frustum_normals",
-                 "compute_projection", "project"):
+                 "points_in_frustum", "compute_projection", "project"):
         assert params(getattr(ProjectionHelper, name)) == params(getattr(ref.ProjectionHelper, name)), name
     assert hasattr(ProjectionHelper, "compute_projection_views") and hasattr(ProjectionHelper, "project_views")
+    from situation3d_b200.projection import Projection
+    assert params(Projection.forward) == params(ref.Projection.forward)
 
 
 def test_voxel_pe_and_projection_reject_cpu_tensors():

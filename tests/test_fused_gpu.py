@@ -580,7 +580,15 @@ def test_projection_vs_reference_class():
         assert cc.shape == (8, 4, 1)
         np.testing.assert_allclose(cc.squeeze(-1).cpu().numpy(), g["corners"][v], rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(helper.compute_frustum_normals(cc).cpu().numpy(), g["normals"][v], rtol=1e-4, atol=1e-4)
+        # points_in_frustum on the reference's own corners / normals: mask and count
+        want = np.unpackbits(g["frustum_masks"][v])[:n].astype(bool)
+        rc, rn = torch.from_numpy(g["corners"][v]).cuda().unsqueeze(2), torch.from_numpy(g["normals"][v]).cuda()
+        mask = helper.points_in_frustum(rc, rn, points.cpu(), return_mask=True)
+        assert mask.dtype == torch.bool and np.array_equal(mask.cpu().numpy(), want)
+        assert int(helper.points_in_frustum(rc, rn, points)) == int(want.sum())
     label = torch.from_numpy(g["label"]).cuda()
+    from situation3d_b200.projection import Projection
+    assert torch.equal(Projection.apply(label[3], i3[3], i2[3], n), helper.project(label[3], i3[3], i2[3], n))
     out = helper.project(label[3], i3[3], i2[3], n)
     assert out.shape == (label.shape[1], n) and np.array_equal(out.cpu().numpy(), g["project_view3"])
     allv = helper.project_views(label, i3, i2, n)

@@ -315,6 +315,10 @@ def test_projection_oracle_vs_reference_class():
         np.testing.assert_allclose(corners.numpy(), g["corners"][v], rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(normals.numpy(), g["normals"][v], rtol=1e-4, atol=1e-4)
     assert seen_none
+    for v in range(nviews):                                  # points_in_frustum with the reference's own corners / normals
+        want = np.unpackbits(g["frustum_masks"][v])[:n].astype(bool)
+        assert np.array_equal(orc.points_in_frustum(g["corners"][v], g["normals"][v], points, True).numpy(), want)
+        assert orc.points_in_frustum(g["corners"][v], g["normals"][v], points) == int(want.sum())
     out = orc.project(g["label"][3], g["indices_3d"][3], g["indices_2d"][3], n)
     assert np.array_equal(out, g["project_view3"])
     for v in range(nviews):
