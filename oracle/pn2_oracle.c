@@ -16,7 +16,7 @@
  * Parity pinning: the reference ships no golden vectors for this path
  * (SURVEY.md section 4).  The oracle is pinned against the reference's own CUDA
  * extension, built unmodified from /root/reference into oracle/_ref/ by
- * oracle/build_ref.py and executed on the GPU box (tests/test_ref_parity.py),
+ * oracle/build_ref.py and executed on the GPU box (tests/test_ops_gpu.py::test_against_reference_cuda_kernels_full_size),
  * and against the fixtures those runs produced (tests/golden/).
  */
 #include <math.h>
