@@ -130,6 +130,21 @@ int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *
 int pn2_furthest_point_sampling_rows(int b, int n, int m, const float *rows, int pitch, int *idxs,
                                      float *new_xyz, float *xyz_copy, pn2_stream_t stream);
 
+/* Same two entry points with a workspace of pn2_furthest_point_sampling_workspace_bytes(b, n, m) bytes (16-byte
+ * aligned device memory, no initialisation needed).  Scenes of more than 8192 points then run the bucketed kernel
+ * (csrc/fps_bucket.cu: one CTA per scene, points binned into spatial buckets, the distance update pruned exactly
+ * by bounding boxes); without a workspace, or for small scenes, the register-resident kernels of csrc/fps.cu run.
+ * Results are identical either way. */
+int pn2_furthest_point_sampling_xyz_ws(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
+                                       void *workspace, size_t workspace_bytes, pn2_stream_t stream);
+int pn2_furthest_point_sampling_rows_ws(int b, int n, int m, const float *rows, int pitch, int *idxs,
+                                        float *new_xyz, float *xyz_copy, void *workspace, size_t workspace_bytes,
+                                        pn2_stream_t stream);
+/* Diagnostic for the bucketed kernel: prof (device, 6 x int64) = SM cycles of thread 0 of CTA 0 spent in
+ * {bucket tests, bucket updates, thread/warp argmax, barrier, table argmax, -}, summed over the rounds. */
+int pn2_debug_fps_bucket_profile(int b, int n, int m, const float *xyz, int *idxs, long long *prof,
+                                 void *workspace, size_t workspace_bytes, pn2_stream_t stream);
+
 /* Diagnostic: same launch as pn2_furthest_point_sampling; prof (device, 5 x int64) receives the SM cycles
  * thread 0 of CTA 0 spent per phase of a round, summed over the m-1 rounds. */
 int pn2_debug_fps_profile(int b, int n, int m, const float *xyz, int *idxs, long long *prof,

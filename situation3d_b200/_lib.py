@@ -48,6 +48,9 @@ _PROTOTYPES = {
     "pn2_furthest_point_sampling": (_i, [_i, _i, _i, _p, _p, c_size_t, _p, _p]),
     "pn2_furthest_point_sampling_xyz": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "pn2_furthest_point_sampling_rows": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "pn2_furthest_point_sampling_xyz_ws": (_i, [_i, _i, _i, _p, _p, _p, _p, c_size_t, _p]),
+    "pn2_furthest_point_sampling_rows_ws": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _p, c_size_t, _p]),
+    "pn2_debug_fps_bucket_profile": (_i, [_i, _i, _i, _p, _p, _p, _p, c_size_t, _p]),
     "pn2_debug_fps_profile": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "pn2_three_nn": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
     "pn2_three_interpolate": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),

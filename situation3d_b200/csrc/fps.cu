@@ -33,6 +33,12 @@
 
 namespace pn2 {
 
+// fps_bucket.cu: one CTA per scene over spatially bucketed points (large scenes, needs a workspace)
+int fps_bucket_min_points();
+size_t fps_bucket_workspace_bytes(int b, int n);
+int fps_bucket_launch(int b, int n, int m, int lg_bs, int cnt, const float *xyz, int pitch, int *idxs, float *new_xyz,
+                      float *xyz_copy, void *ws, size_t ws_bytes, long long *prof, cudaStream_t stream);
+
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;
@@ -409,7 +415,10 @@ static bool make_plan(int n, FpsPlan *pl)
         const int v = atoi(e);
         if (v == 128 || v == 256 || v == 512) threads = v;
     }
-    const long long per = (slots + (long long)cluster * threads - 1) / ((long long)cluster * threads);
+    long long per = (slots + (long long)cluster * threads - 1) / ((long long)cluster * threads);
+    // 40 slots per thread exist only for 128-thread clusters (dispatch): wider CTAs take at most 32
+    if (per > 32 && threads == 256) { threads = 512; per = (slots + (long long)cluster * threads - 1) / ((long long)cluster * threads); }
+    if (per > 32 && !(threads == 128 && cluster > 1)) return false;
     int ppt = -1;
     for (int v : kPpt)
         if (v >= per) { ppt = v; break; }
@@ -491,10 +500,13 @@ static int dispatch(const FpsPlan &pl, int b, int n, int m, const float *xyz, in
 
 using namespace pn2;
 
-extern "C" size_t pn2_furthest_point_sampling_workspace_bytes(int, int, int) { return 0; }
+extern "C" size_t pn2_furthest_point_sampling_workspace_bytes(int b, int n, int)
+{
+    return b > 0 ? fps_bucket_workspace_bytes(b, n) : 0;
+}
 
 static int fps_entry(int b, int n, int m, const float *xyz, int pitch, int *idxs, float *new_xyz, float *xyz_copy,
-                     long long *prof, pn2_stream_t stream)
+                     long long *prof, pn2_stream_t stream, void *ws = nullptr, size_t ws_bytes = 0)
 {
     if (b < 0 || n < 0 || m < 0 || pitch < 3) return PN2_ERR_INVALID_ARGUMENT;
     if (b == 0 || m == 0) return PN2_OK;
@@ -507,8 +519,15 @@ static int fps_entry(int b, int n, int m, const float *xyz, int pitch, int *idxs
         return PN2_OK;
     }
     if (!xyz) return PN2_ERR_INVALID_ARGUMENT;
+    // large scenes with a workspace: spatially bucketed points, one CTA per scene (fps_bucket.cu)
+    const size_t need = fps_bucket_workspace_bytes(b, n);
+    if (ws && need && ws_bytes >= need) {
+        const int lg = ref_block_lg(n), bs = 1 << lg;
+        return fps_bucket_launch(b, n, m, lg, (n + bs - 1) / bs, xyz, pitch, idxs, new_xyz, xyz_copy, ws, ws_bytes, prof,
+                                 as_stream(stream));
+    }
     FpsPlan pl;
-    if (!make_plan(n, &pl)) return PN2_ERR_INVALID_ARGUMENT;   // n > 16 CTAs x 512 threads x 32 slots
+    if (!make_plan(n, &pl)) return PN2_ERR_INVALID_ARGUMENT;   // n > 16 CTAs x 512 threads x 40 slots: needs the workspace
     return dispatch(pl, b, n, m, xyz, pitch, idxs, new_xyz, xyz_copy, prof, as_stream(stream));
 }
 
@@ -535,8 +554,30 @@ extern "C" int pn2_debug_fps_profile(int b, int n, int m, const float *xyz, int 
     return fps_entry(b, n, m, xyz, 3, idxs, nullptr, nullptr, prof, stream);
 }
 
-extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, void *, size_t,
+extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, void *workspace, size_t workspace_bytes,
                                            int *idxs, pn2_stream_t stream)
 {
-    return pn2_furthest_point_sampling_xyz(b, n, m, xyz, idxs, nullptr, stream);
+    return fps_entry(b, n, m, xyz, 3, idxs, nullptr, nullptr, nullptr, stream, workspace, workspace_bytes);
+}
+
+extern "C" int pn2_furthest_point_sampling_xyz_ws(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
+                                                  void *workspace, size_t workspace_bytes, pn2_stream_t stream)
+{
+    return fps_entry(b, n, m, xyz, 3, idxs, new_xyz, nullptr, nullptr, stream, workspace, workspace_bytes);
+}
+
+extern "C" int pn2_furthest_point_sampling_rows_ws(int b, int n, int m, const float *rows, int pitch, int *idxs,
+                                                   float *new_xyz, float *xyz_copy, void *workspace, size_t workspace_bytes,
+                                                   pn2_stream_t stream)
+{
+    return fps_entry(b, n, m, rows, pitch, idxs, new_xyz, xyz_copy, nullptr, stream, workspace, workspace_bytes);
+}
+
+// Diagnostic for the bucketed kernel: prof (device, 6 x int64) = SM cycles of thread 0 of CTA 0 in {bucket tests,
+// bucket updates, thread/warp argmax, barrier, table argmax, -} summed over the rounds.
+extern "C" int pn2_debug_fps_bucket_profile(int b, int n, int m, const float *xyz, int *idxs, long long *prof,
+                                            void *workspace, size_t workspace_bytes, pn2_stream_t stream)
+{
+    if (!prof) return PN2_ERR_INVALID_ARGUMENT;
+    return fps_entry(b, n, m, xyz, 3, idxs, nullptr, nullptr, prof, stream, workspace, workspace_bytes);
 }

@@ -1,0 +1,513 @@
+// fps_bucket.cu -- furthest point sampling for large scenes: ONE CTA per scene, points binned into spatial
+// buckets, exact pruning of the distance update.  Bit-exact with the reference kernel
+// (lib/pointnet2/_ext_src/src/sampling_gpu.cu:69-173, init sampling.cpp:70-76).
+//
+// Why.  FPS is m-1 dependent rounds: temp[k] = min(temp[k], |p_k - last|^2) for every point, then an argmax.
+// The cluster kernel of fps.cu keeps every point in a register and pays a DSMEM exchange per round over 8 CTAs
+// (~1300 cycles per round, four SMs' worth of registers per scene).  But a round only CHANGES the points closer
+// to the new sample than their running distance -- after a few dozen samples that is a small neighbourhood.
+//
+// How.  The prologue bins the scene's points into a 32^3 Morton grid (shared-memory histogram, counting sort
+// into a workspace; the order inside a cell is irrelevant to the result) and cuts the sorted list into buckets of
+// 32*PPL points; CH consecutive buckets form a super-bucket owned by one thread, which keeps in REGISTERS the
+// bounding boxes, each bucket's largest running distance and that candidate's index and coordinates.  A round:
+//   1. every thread tests its super-bucket (then its CH buckets) against the new sample: with
+//      lb = |max(lo - s, s - hi, 0)|^2 evaluated by the same FSUB/FMUL/FFMA/FFMA recipe as the point distances,
+//      lb <= d_k holds in fp32 for every point k of the box (rounding is monotonic), so lb >= bucket max means
+//      min(d_k, temp[k]) == temp[k] for all of them: the bucket is skipped EXACTLY (NaN / inf coordinates never
+//      lower a distance in the reference either: fminf drops a NaN, and they are left out of the boxes);
+//   2. the owning warp streams each surviving bucket (float4 x,y,z,index per point from L2, running distances in
+//      shared memory), updates the distances and, if any changed, re-derives the bucket's candidate
+//      (redux.sync max on the distance bits; ties by the reference's order, below);
+//   3. argmax over the threads' cached candidates: warp redux -> 16-entry table -> one bar.sync -> every warp
+//      reduces the table.
+// About 35 full passes' worth of point updates for 2047 rounds over 40 000 points instead of 2047 passes.
+//
+// Tie order.  The reference's strided scan + shared-memory tree picks, among equal maxima, the smallest
+// "rank" g(k) = bitrev(k mod bs) * cnt + k div bs (fps.cu).  Equal keys are rare (duplicate
+// points), so every comparison is on the distance bits first and evaluates g only on a tie.
+#include "common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace pn2 {
+namespace {
+
+constexpr int kBT = 512;              // threads per CTA
+constexpr int kBW = kBT / 32;         // warps
+constexpr int kCellBits = 5;
+constexpr int kCells = 1 << (3 * kCellBits);
+constexpr int kCellsPerWarp = kCells / kBW;
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr uint32_t kSkipCell = 0xffffu;
+constexpr size_t kMaxSmem = 227 * 1024 - 2048;
+
+// order-preserving map float -> uint32 (for redux.sync min / max over signed floats)
+__device__ __forceinline__ uint32_t ord_key(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float ord_inv(uint32_t k)
+{
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ uint32_t spread5(uint32_t v)   // bit i -> bit 3i (5 bits)
+{
+    v = (v | (v << 8)) & 0x100fu;
+    v = (v | (v << 4)) & 0x10c3u;
+    v = (v | (v << 2)) & 0x1249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t rank_of(uint32_t k, int lg_bs, int cnt)
+{
+    const uint32_t t = k & ((1u << lg_bs) - 1u);
+    const uint32_t bt = lg_bs ? (__brev(t) >> (32 - lg_bs)) : 0u;
+    return bt * (uint32_t)cnt + (k >> lg_bs);
+}
+__device__ __forceinline__ bool finite3(float x, float y, float z)
+{
+    return fabsf(x) < INFINITY && fabsf(y) < INFINITY && fabsf(z) < INFINITY;
+}
+// squared distance from s to the box [lo, hi], a lower bound (in fp32, same recipe as sqdist3) of the
+// squared distance from s to any point inside the box
+__device__ __forceinline__ float box_lb(float lx, float ly, float lz, float hx, float hy, float hz, float sx, float sy, float sz)
+{
+    const float dx = fmaxf(fmaxf(__fsub_rn(lx, sx), __fsub_rn(sx, hx)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rn(ly, sy), __fsub_rn(sy, hy)), 0.f);
+    const float dz = fmaxf(fmaxf(__fsub_rn(lz, sz), __fsub_rn(sz, hz)), 0.f);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+__device__ __forceinline__ uint32_t dist_key(float d) { return d >= 0.f ? __float_as_uint(d) + 1u : 0u; }
+__device__ __forceinline__ float key_dist(uint32_t k) { return k ? __uint_as_float(k - 1u) : -1.f; }
+
+struct Cand {            // argmax candidate: key (0 = none), original point index, coordinates
+    uint32_t key, idx;
+    float x, y, z;
+};
+// a > b in the reference's order (larger distance, then smaller rank); evaluates ranks only on a tie
+__device__ __forceinline__ bool cand_better(uint32_t ak, uint32_t ai, uint32_t bk, uint32_t bi, int lg_bs, int cnt)
+{
+    if (ak != bk) return ak > bk;
+    if (ak == 0u) return false;
+    return rank_of(ai, lg_bs, cnt) < rank_of(bi, lg_bs, cnt);
+}
+// warp argmax of per-lane candidates; the result is in every lane
+__device__ __forceinline__ Cand warp_best(const Cand &c, int lg_bs, int cnt)
+{
+    const uint32_t kmax = __reduce_max_sync(kFullMask, c.key);
+    const unsigned eqm = __ballot_sync(kFullMask, c.key == kmax);
+    int src = __ffs(eqm) - 1;
+    if (kmax != 0u && (eqm & (eqm - 1u))) {      // several lanes hold the maximum: smallest rank wins
+        const uint32_t r = c.key == kmax ? rank_of(c.idx, lg_bs, cnt) : 0xffffffffu;
+        const uint32_t rm = __reduce_min_sync(kFullMask, r);
+        src = __ffs(__ballot_sync(kFullMask, r == rm)) - 1;
+    }
+    Cand w;
+    w.key = kmax;
+    w.idx = __shfl_sync(kFullMask, c.idx, src);
+    w.x = __shfl_sync(kFullMask, c.x, src);
+    w.y = __shfl_sync(kFullMask, c.y, src);
+    w.z = __shfl_sync(kFullMask, c.z, src);
+    return w;
+}
+
+// PPL points per lane in a bucket (bucket = 32*PPL points), CH buckets per super-bucket, SS super-buckets per
+// thread; SDIST: running distances in shared memory (else in the workspace).
+template <int PPL, int CH, int SS, bool SDIST>
+__global__ void __launch_bounds__(kBT, 1)
+fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int pitch, int *__restrict__ idxs,
+                  float *__restrict__ new_xyz, float *__restrict__ xyz_copy, unsigned char *__restrict__ ws,
+                  size_t ws_stride, int npad, long long *__restrict__ prof)
+{
+    constexpr int BS = 32 * PPL;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(dyn);     // prologue: cell histogram / offsets
+    __shared__ uint32_t red[kBW][8];
+    __shared__ uint32_t wbase[kBW + 1];
+    __shared__ __align__(16) uint4 table[2][kBW];            // per round parity: (key, x, y, z) of every warp's winner
+    __shared__ uint32_t table_i[2][kBW];                     //                   its point index
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int scene = blockIdx.x;
+    const float *p = xyz + (size_t)scene * n * pitch;
+    float *cp = xyz_copy ? xyz_copy + (size_t)scene * n * 3 : nullptr;
+    int *out_idx = idxs + (size_t)scene * m;
+    float *out_xyz = new_xyz ? new_xyz + (size_t)scene * m * 3 : nullptr;
+    unsigned char *w = ws + (size_t)scene * ws_stride;
+    float4 *pts = reinterpret_cast<float4 *>(w);                                  // npad x (x, y, z, index)
+    float *dist = SDIST ? reinterpret_cast<float *>(dyn) : reinterpret_cast<float *>(w + (size_t)16 * npad);
+    unsigned short *cellid = reinterpret_cast<unsigned short *>(w + (size_t)20 * npad);
+
+    for (int i = tid; i < kCells; i += kBT) hist[i] = 0u;
+
+    // ---- P1: bounding box of the competing, finite points (+ the contiguous xyz copy) -----------------------
+    const bool vec4 = (pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 4
+    for (int k = tid; k < n; k += kBT) {
+        float x, y, z;
+        if (vec4) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p + (size_t)pitch * k));
+            x = v.x; y = v.y; z = v.z;
+        } else {
+            x = __ldg(p + (size_t)pitch * k); y = __ldg(p + (size_t)pitch * k + 1); z = __ldg(p + (size_t)pitch * k + 2);
+        }
+        if (cp) { cp[3 * (size_t)k] = x; cp[3 * (size_t)k + 1] = y; cp[3 * (size_t)k + 2] = z; }
+        // sampling_gpu.cu:100-101: float mag compared against the double literal 1e-3
+        const bool skip = (double)sqnorm3(x, y, z) <= 1e-3;
+        if (!skip && finite3(x, y, z)) {
+            mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+            mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const uint32_t lo = __reduce_min_sync(kFullMask, ord_key(mn[a]));
+        const uint32_t hi = __reduce_max_sync(kFullMask, ord_key(mx[a]));
+        if (lane == 0) { red[warp][a] = lo; red[warp][3 + a] = hi; }
+    }
+    __syncthreads();
+    float lo3[3], ext = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const uint32_t lo = __reduce_min_sync(kFullMask, lane < kBW ? red[lane][a] : 0xffffffffu);
+        const uint32_t hi = __reduce_max_sync(kFullMask, lane < kBW ? red[lane][3 + a] : 0u);
+        lo3[a] = ord_inv(lo);
+        ext = fmaxf(ext, ord_inv(hi) - lo3[a]);          // -inf when there is no finite point
+    }
+    const float scale = (ext > 0.f && ext < INFINITY) ? (float)(1 << kCellBits) / ext : 0.f;
+    if (!(fabsf(lo3[0]) < INFINITY)) { lo3[0] = lo3[1] = lo3[2] = 0.f; }
+
+    // ---- P2: Morton cell of every point, histogram ----------------------------------------------------------
+    const float *src = cp ? cp : p;
+    const int sp = cp ? 3 : pitch;
+    constexpr float kQMax = (float)((1 << kCellBits) - 1);
+#pragma unroll 4
+    for (int k = tid; k < n; k += kBT) {
+        const float x = src[(size_t)sp * k], y = src[(size_t)sp * k + 1], z = src[(size_t)sp * k + 2];
+        uint32_t c = kSkipCell;
+        if (!((double)sqnorm3(x, y, z) <= 1e-3)) {
+            const uint32_t qx = (uint32_t)fminf(fmaxf((x - lo3[0]) * scale, 0.f), kQMax);
+            const uint32_t qy = (uint32_t)fminf(fmaxf((y - lo3[1]) * scale, 0.f), kQMax);
+            const uint32_t qz = (uint32_t)fminf(fmaxf((z - lo3[2]) * scale, 0.f), kQMax);
+            c = spread5(qx) | (spread5(qy) << 1) | (spread5(qz) << 2);
+            atomicAdd(&hist[c], 1u);
+        }
+        cellid[k] = (unsigned short)c;
+    }
+    __syncthreads();
+
+    // ---- P3: exclusive scan of the histogram (each warp scans its 2048 cells; warp bases added on use) ------
+    {
+        uint32_t carry = 0;
+        const int c0 = warp * kCellsPerWarp;
+        for (int i = 0; i < kCellsPerWarp; i += 32) {
+            const uint32_t v = hist[c0 + i + lane];
+            uint32_t inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+                if (lane >= d) inc += t;
+            }
+            hist[c0 + i + lane] = carry + inc - v;
+            carry += __shfl_sync(kFullMask, inc, 31);
+        }
+        if (lane == 0) red[warp][6] = carry;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = lane < kBW ? red[lane][6] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane < kBW) wbase[lane] = inc - v;
+        if (lane == kBW - 1) wbase[kBW] = inc;
+    }
+    __syncthreads();
+    const int nv = (int)wbase[kBW];                      // points that compete (not skipped)
+
+    // ---- P4: counting sort into the workspace ---------------------------------------------------------------
+#pragma unroll 4
+    for (int k = tid; k < n; k += kBT) {
+        const uint32_t c = cellid[k];
+        if (c != kSkipCell) {
+            const uint32_t pos = atomicAdd(&hist[c], 1u) + wbase[c / kCellsPerWarp];
+            pts[pos] = make_float4(src[(size_t)sp * k], src[(size_t)sp * k + 1], src[(size_t)sp * k + 2], __int_as_float(k));
+        }
+    }
+    __syncthreads();                                     // histogram dead from here: `dist` may alias it
+
+    // ---- P5: running distances, bucket boxes and first candidates into registers ----------------------------
+    // bucket (ss, l, c) of warp w = global bucket (((ss*32 + l)*kBW + w)*CH + c): neighbouring super-buckets
+    // belong to different warps, so the few active ones of a round spread over the warps
+    float slo[SS][3], shi[SS][3], smax[SS];
+    float clo[SS][CH][3], chi[SS][CH][3], cmx[SS][CH];
+    uint32_t cki[SS][CH];
+    float ccx[SS][CH], ccy[SS][CH], ccz[SS][CH];
+#pragma unroll
+    for (int ss = 0; ss < SS; ++ss) {
+        smax[ss] = -1.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { slo[ss][a] = INFINITY; shi[ss][a] = -INFINITY; }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            cmx[ss][c] = -1.f; cki[ss][c] = 0u; ccx[ss][c] = ccy[ss][c] = ccz[ss][c] = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { clo[ss][c][a] = INFINITY; chi[ss][c][a] = -INFINITY; }
+        }
+    }
+#pragma unroll
+    for (int ss = 0; ss < SS; ++ss) {
+        for (int l = 0; l < 32; ++l) {
+            const long long sup = (long long)(ss * 32 + l) * kBW + warp;
+            if (sup * CH * BS >= nv) break;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const long long base = (sup * CH + c) * BS;
+                if (base >= nv) continue;
+                Cand best; best.key = 0u; best.idx = 0u; best.x = best.y = best.z = 0.f;
+                float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const long long pos = base + q * 32 + lane;
+                    float4 pt = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+                    float d = -1.f;
+                    if (pos < nv) { pt = pts[pos]; d = 1e10f; }                     // sampling.cpp:74-76
+                    else pts[pos] = pt;                                             // padding: never a candidate
+                    dist[pos] = d;
+                    if (pos < nv && finite3(pt.x, pt.y, pt.z)) {
+                        bl[0] = fminf(bl[0], pt.x); bl[1] = fminf(bl[1], pt.y); bl[2] = fminf(bl[2], pt.z);
+                        bh[0] = fmaxf(bh[0], pt.x); bh[1] = fmaxf(bh[1], pt.y); bh[2] = fmaxf(bh[2], pt.z);
+                    }
+                    const uint32_t key = dist_key(d), pi = (uint32_t)__float_as_int(pt.w);
+                    if (cand_better(key, pi, best.key, best.idx, lg_bs, cnt)) { best.key = key; best.idx = pi; best.x = pt.x; best.y = pt.y; best.z = pt.z; }
+                }
+                const Cand wb = warp_best(best, lg_bs, cnt);
+                float rl[3], rh[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    rl[a] = ord_inv(__reduce_min_sync(kFullMask, ord_key(bl[a])));
+                    rh[a] = ord_inv(__reduce_max_sync(kFullMask, ord_key(bh[a])));
+                }
+                if (lane == l) {
+                    cmx[ss][c] = key_dist(wb.key); cki[ss][c] = wb.idx; ccx[ss][c] = wb.x; ccy[ss][c] = wb.y; ccz[ss][c] = wb.z;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        clo[ss][c][a] = rl[a]; chi[ss][c][a] = rh[a];
+                        slo[ss][a] = fminf(slo[ss][a], rl[a]); shi[ss][a] = fmaxf(shi[ss][a], rh[a]);
+                    }
+                    smax[ss] = fmaxf(smax[ss], cmx[ss][c]);
+                }
+            }
+        }
+    }
+
+    // sampling_gpu.cu:85-87: the first sample is point 0, unconditionally
+    const float p0x = __ldg(p), p0y = __ldg(p + 1), p0z = __ldg(p + 2);
+    float ox = p0x, oy = p0y, oz = p0z;
+    if (tid == 0) {
+        out_idx[0] = 0;
+        if (out_xyz) { out_xyz[0] = ox; out_xyz[1] = oy; out_xyz[2] = oz; }
+    }
+    __syncthreads();
+
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
+    const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
+    if (profiling) tprev = clock64();
+#define PN2_FPSB_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
+
+    struct Buf { float4 p[PPL]; float d[PPL]; };
+
+    for (int j = 1; j < m; ++j) {
+        const int par = j & 1;
+        // ---- 1. which buckets can change? -------------------------------------------------------------------
+        uint32_t cm[SS];
+#pragma unroll
+        for (int ss = 0; ss < SS; ++ss) {
+            cm[ss] = 0u;
+            if (box_lb(slo[ss][0], slo[ss][1], slo[ss][2], shi[ss][0], shi[ss][1], shi[ss][2], ox, oy, oz) < smax[ss]) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    if (box_lb(clo[ss][c][0], clo[ss][c][1], clo[ss][c][2], chi[ss][c][0], chi[ss][c][1], chi[ss][c][2], ox, oy, oz) < cmx[ss][c])
+                        cm[ss] |= 1u << c;
+            }
+        }
+        PN2_FPSB_MARK(0)
+        // ---- 2. the owning warp updates them, two buckets in flight -----------------------------------------
+#pragma unroll
+        for (int ss = 0; ss < SS; ++ss) {
+            unsigned sm = __ballot_sync(kFullMask, cm[ss] != 0u);
+            if (sm == 0u) continue;
+            uint32_t cur = 0u;       // children still to do of lane `cl`
+            int cl = 0;
+            auto next = [&](int &l, int &c) -> bool {
+                if (cur == 0u) {
+                    if (sm == 0u) return false;
+                    cl = __ffs(sm) - 1; sm &= sm - 1u;
+                    cur = __shfl_sync(kFullMask, cm[ss], cl);
+                }
+                l = cl; c = __ffs(cur) - 1; cur &= cur - 1u;
+                return true;
+            };
+            auto load = [&](int l, int c, Buf &b) {
+                const uint32_t base = (uint32_t)((((ss * 32 + l) * kBW + warp) * CH + c) * BS);
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) { b.p[q] = pts[base + q * 32 + lane]; b.d[q] = dist[base + q * 32 + lane]; }
+            };
+            auto process = [&](int l, int c, const Buf &b) {
+                const uint32_t base = (uint32_t)((((ss * 32 + l) * kBW + warp) * CH + c) * BS);
+                float nd[PPL];
+                bool ch = false;
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    nd[q] = fminf(sqdist3(b.p[q].x, b.p[q].y, b.p[q].z, ox, oy, oz), b.d[q]);   // sampling_gpu.cu:104-107
+                    ch |= nd[q] != b.d[q];
+                }
+                if (!__any_sync(kFullMask, ch)) return;
+                Cand best; best.key = 0u; best.idx = 0u; best.x = best.y = best.z = 0.f;
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    if (nd[q] != b.d[q]) dist[base + q * 32 + lane] = nd[q];
+                    const uint32_t key = dist_key(nd[q]), pi = (uint32_t)__float_as_int(b.p[q].w);
+                    if (cand_better(key, pi, best.key, best.idx, lg_bs, cnt)) { best.key = key; best.idx = pi; best.x = b.p[q].x; best.y = b.p[q].y; best.z = b.p[q].z; }
+                }
+                const Cand wb = warp_best(best, lg_bs, cnt);
+                if (lane == l) {
+#pragma unroll
+                    for (int cc = 0; cc < CH; ++cc)
+                        if (cc == c) { cmx[ss][cc] = key_dist(wb.key); cki[ss][cc] = wb.idx; ccx[ss][cc] = wb.x; ccy[ss][cc] = wb.y; ccz[ss][cc] = wb.z; }
+                }
+            };
+            Buf A, B;
+            int la, ca, lb, cb;
+            bool ha = next(la, ca), hb;
+            if (ha) load(la, ca, A);
+            while (ha) {
+                hb = next(lb, cb);
+                if (hb) load(lb, cb, B);
+                process(la, ca, A);
+                if (!hb) break;
+                ha = next(la, ca);
+                if (ha) load(la, ca, A);
+                process(lb, cb, B);
+            }
+            float s = cmx[ss][0];
+#pragma unroll
+            for (int c = 1; c < CH; ++c) s = fmaxf(s, cmx[ss][c]);
+            smax[ss] = s;
+        }
+        PN2_FPSB_MARK(1)
+        // ---- 3. argmax: thread -> warp -> table -> every warp -----------------------------------------------
+        Cand tb; tb.key = 0u; tb.idx = 0u; tb.x = tb.y = tb.z = 0.f;
+#pragma unroll
+        for (int ss = 0; ss < SS; ++ss)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const uint32_t key = dist_key(cmx[ss][c]);
+                if (cand_better(key, cki[ss][c], tb.key, tb.idx, lg_bs, cnt)) { tb.key = key; tb.idx = cki[ss][c]; tb.x = ccx[ss][c]; tb.y = ccy[ss][c]; tb.z = ccz[ss][c]; }
+            }
+        const Cand wb = warp_best(tb, lg_bs, cnt);
+        if (lane == 0) {
+            table[par][warp] = make_uint4(wb.key, __float_as_uint(wb.x), __float_as_uint(wb.y), __float_as_uint(wb.z));
+            table_i[par][warp] = wb.idx;
+        }
+        PN2_FPSB_MARK(2)
+        __syncthreads();
+        PN2_FPSB_MARK(3)
+        Cand e; e.key = 0u; e.idx = 0u; e.x = e.y = e.z = 0.f;
+        if (lane < kBW) {
+            const uint4 t = table[par][lane];
+            e.key = t.x; e.x = __uint_as_float(t.y); e.y = __uint_as_float(t.z); e.z = __uint_as_float(t.w);
+            e.idx = table_i[par][lane];
+        }
+        const Cand win = warp_best(e, lg_bs, cnt);
+        const bool none = win.key == 0u;   // every point skipped: the reference's reduction leaves besti = 0
+        ox = none ? p0x : win.x; oy = none ? p0y : win.y; oz = none ? p0z : win.z;
+        if (tid == (j & (kBT - 1))) {
+            out_idx[j] = none ? 0 : (int)win.idx;
+            if (out_xyz) { out_xyz[3 * (size_t)j] = ox; out_xyz[3 * (size_t)j + 1] = oy; out_xyz[3 * (size_t)j + 2] = oz; }
+        }
+        PN2_FPSB_MARK(4)
+    }
+    if (profiling)
+        for (int i = 0; i < 6; ++i) prof[i] = pc[i];
+#undef PN2_FPSB_MARK
+}
+
+struct BucketCfg {
+    int ppl, ss;
+    bool sdist;
+    int npad;
+    size_t smem, stride;
+};
+
+constexpr int kCH = 4;
+
+bool choose(int n, BucketCfg *c)
+{
+    if (n <= 0) return false;
+    int ppl, ss = 1;
+    if (n <= kBT * kCH * 32) ppl = 1;
+    else if (n <= kBT * kCH * 64) ppl = 2;
+    else if (n <= kBT * kCH * 128) ppl = 4;
+    else if (n <= 2 * kBT * kCH * 128) { ppl = 4; ss = 2; }
+    else return false;
+    const int bs = 32 * ppl;
+    c->ppl = ppl; c->ss = ss;
+    c->npad = (n + bs - 1) / bs * bs;
+    c->sdist = (size_t)c->npad * 4 <= kMaxSmem;
+    const size_t h = (size_t)kCells * 4;
+    c->smem = c->sdist && (size_t)c->npad * 4 > h ? (size_t)c->npad * 4 : h;
+    const size_t bytes = (size_t)20 * c->npad + (size_t)2 * n;
+    c->stride = (bytes + 255) / 256 * 256;
+    return true;
+}
+
+template <int PPL, int SS, bool SDIST>
+int launch_cfg(const BucketCfg &c, int b, int n, int m, int lg_bs, int cnt, const float *xyz, int pitch, int *idxs,
+               float *new_xyz, float *xyz_copy, void *ws, long long *prof, cudaStream_t stream)
+{
+    auto kern = fps_bucket_kernel<PPL, kCH, SS, SDIST>;
+    PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    kern<<<b, kBT, c.smem, stream>>>(n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy,
+                                     static_cast<unsigned char *>(ws), c.stride, c.npad, prof);
+    PN2_LAUNCH_CHECK("fps_bucket_kernel");
+    return PN2_OK;
+}
+
+}  // namespace
+
+// smallest scene the bucketed kernel is used for (below, the register-resident kernels of fps.cu win)
+int fps_bucket_min_points()
+{
+    const char *e = getenv("PN2_FPS_BUCKET_MIN");    // tests / sweeps: 1 = always, a huge value = never
+    return e ? atoi(e) : 8193;
+}
+
+size_t fps_bucket_workspace_bytes(int b, int n)
+{
+    BucketCfg c;
+    if (n < fps_bucket_min_points() || !choose(n, &c)) return 0;
+    return c.stride * (size_t)b;
+}
+
+int fps_bucket_launch(int b, int n, int m, int lg_bs, int cnt, const float *xyz, int pitch, int *idxs, float *new_xyz,
+                      float *xyz_copy, void *ws, size_t ws_bytes, long long *prof, cudaStream_t stream)
+{
+    BucketCfg c;
+    if (!choose(n, &c)) return PN2_ERR_INVALID_ARGUMENT;
+    if (!ws || ws_bytes < c.stride * (size_t)b || (reinterpret_cast<uintptr_t>(ws) & 15)) return PN2_ERR_WORKSPACE;
+#define PN2_FPSB_GO(PPL, SS, SD) \
+    return launch_cfg<PPL, SS, SD>(c, b, n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, ws, prof, stream)
+    if (c.ppl == 1) { if (c.sdist) PN2_FPSB_GO(1, 1, true); else PN2_FPSB_GO(1, 1, false); }
+    if (c.ppl == 2) PN2_FPSB_GO(2, 1, false);
+    if (c.ss == 1) PN2_FPSB_GO(4, 1, false);
+    PN2_FPSB_GO(4, 2, false);
+#undef PN2_FPSB_GO
+}
+
+}  // namespace pn2

@@ -198,32 +198,40 @@ def rows_from_channels(features):
     return rows
 
 
+def _fps_workspace(B, N, npoint, device):
+    """Scratch of the bucketed sampling kernel (csrc/fps_bucket.cu), from PyTorch's caching allocator; None for
+    small scenes (register-resident kernels)."""
+    nbytes = lib.pn2_furthest_point_sampling_workspace_bytes(B, N, npoint)
+    return (torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes) if nbytes else (None, 0)
+
+
 def fps_with_xyz(xyz, npoint):
     """Furthest point sampling that also returns new_xyz = xyz[inds] (B,npoint,3)."""
     B, N, _ = xyz.shape
     inds = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
     new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
-        check(lib.pn2_furthest_point_sampling_xyz(B, N, npoint, ptr(xyz), ptr(inds), ptr(new_xyz), stream_ptr()),
-              "furthest_point_sampling_xyz")
+    fps_into(xyz, inds, new_xyz)
     return inds, new_xyz
 
 
 def fps_into(xyz, inds, new_xyz):
     """Same, into caller-allocated outputs (used by the backbone's side-stream sampling pyramid)."""
     B, N, _ = xyz.shape
+    ws, nbytes = _fps_workspace(B, N, inds.shape[1], xyz.device)
     with torch.cuda.device(xyz.device):
-        check(lib.pn2_furthest_point_sampling_xyz(B, N, inds.shape[1], ptr(xyz), ptr(inds), ptr(new_xyz),
-                                                  stream_ptr()), "furthest_point_sampling_xyz")
+        check(lib.pn2_furthest_point_sampling_xyz_ws(B, N, inds.shape[1], ptr(xyz), ptr(inds), ptr(new_xyz), ptr(ws),
+                                                     nbytes, stream_ptr()), "furthest_point_sampling_xyz")
 
 
 def fps_rows_into(rows, inds, new_xyz, xyz_copy):
     """Sampling straight from (B, N, pitch) rows whose first three floats are xyz (``point_clouds`` in place); also
     fills ``xyz_copy`` (B, N, 3), the contiguous coordinates the later kernels read."""
     B, N, pitch = rows.shape
+    ws, nbytes = _fps_workspace(B, N, inds.shape[1], rows.device)
     with torch.cuda.device(rows.device):
-        check(lib.pn2_furthest_point_sampling_rows(B, N, inds.shape[1], ptr(rows), pitch, ptr(inds), ptr(new_xyz),
-                                                   ptr(xyz_copy), stream_ptr()), "furthest_point_sampling_rows")
+        check(lib.pn2_furthest_point_sampling_rows_ws(B, N, inds.shape[1], ptr(rows), pitch, ptr(inds), ptr(new_xyz),
+                                                      ptr(xyz_copy), ptr(ws), nbytes, stream_ptr()),
+              "furthest_point_sampling_rows")
 
 
 def ball_query(xyz, new_xyz, radius, nsample, out=None):

@@ -76,8 +76,11 @@ def furthest_point_sampling(points, nsamples):
     _f(points, "points")
     B, N = points.size(0), points.size(1)
     out = torch.zeros((B, nsamples), device=points.device, dtype=torch.int32)
+    # scratch like the reference's `temp` (sampling.cpp:74-76): large scenes run the bucketed kernel in it
+    nbytes = lib.pn2_furthest_point_sampling_workspace_bytes(B, N, nsamples)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device) if nbytes else None
     with torch.cuda.device(points.device):
-        check(lib.pn2_furthest_point_sampling(B, N, nsamples, ptr(points), None, 0, ptr(out), stream_ptr()),
+        check(lib.pn2_furthest_point_sampling(B, N, nsamples, ptr(points), ptr(ws), nbytes, ptr(out), stream_ptr()),
               "furthest_point_sampling")
     return out
 

@@ -71,9 +71,56 @@ def test_fps_ties_and_skips(ext):
 def test_fps_every_cluster_shape(ext, monkeypatch, cluster, threads):
     monkeypatch.setenv("PN2_FPS_CLUSTER", str(cluster))
     monkeypatch.setenv("PN2_FPS_THREADS", str(threads))
+    monkeypatch.setenv("PN2_FPS_BUCKET_MIN", "1000000000")      # the register-resident cluster kernels, not the bucketed one
     n = 6000 if cluster == 1 else 12000
     x = cloud(55, 2, n, dup=500, zeros=4)
     assert torch.equal(ext.furthest_point_sampling(x.cuda(), 300).cpu(), orc.furthest_point_sampling(x, 300))
+
+
+@pytest.mark.parametrize("b,n,m", [(1, 1, 1), (2, 7, 5), (2, 33, 33), (2, 300, 64), (3, 1000, 256), (2, 2048, 1024),
+                                   (1, 4097, 300), (1, 20, 40), (2, 9000, 700), (1, 20000, 512), (1, 70000, 300),
+                                   (1, 140000, 200)])
+def test_fps_bucketed_kernel_vs_oracle(ext, monkeypatch, b, n, m):
+    """csrc/fps_bucket.cu (one CTA per scene, exact bounding-box pruning) forced for every size."""
+    monkeypatch.setenv("PN2_FPS_BUCKET_MIN", "1")
+    x = cloud(300 + n, b, n, dup=n // 10, zeros=min(3, n // 4))
+    got = ext.furthest_point_sampling(x.cuda(), m).cpu()
+    assert torch.equal(got, orc.furthest_point_sampling(x, m))
+
+
+def test_fps_bucketed_kernel_edge_cases(ext, monkeypatch):
+    monkeypatch.setenv("PN2_FPS_BUCKET_MIN", "1")
+    g = torch.Generator().manual_seed(7)
+    lattice = torch.randint(-3, 4, (2, 700, 3), generator=g).float() * 0.25     # massive exact ties
+    assert torch.equal(ext.furthest_point_sampling(lattice.cuda(), 200).cpu(), orc.furthest_point_sampling(lattice, 200))
+    big = torch.randint(-6, 7, (1, 12000, 3), generator=g).float() * 0.125      # ties across buckets and warps
+    assert torch.equal(ext.furthest_point_sampling(big.cuda(), 400).cpu(), orc.furthest_point_sampling(big, 400))
+    skip = torch.zeros(1, 64, 3)
+    skip[0, :, 0] = torch.linspace(0, 0.02, 64)                                  # |p|^2 <= 1e-3 everywhere
+    assert torch.equal(ext.furthest_point_sampling(skip.cuda(), 8).cpu(), torch.zeros(1, 8, dtype=torch.int32))
+    same = torch.ones(1, 100, 3)                                                 # all points identical
+    assert torch.equal(ext.furthest_point_sampling(same.cuda(), 10).cpu(), orc.furthest_point_sampling(same, 10))
+    odd = cloud(11, 2, 3000, dup=50, zeros=3)                                    # non-finite coordinates
+    odd[0, 5, 0] = float("nan")
+    odd[0, 77] = float("inf")
+    odd[1, 900, 2] = float("-inf")
+    odd[1, 0, 1] = float("nan")                                                  # the unconditional first sample
+    assert torch.equal(ext.furthest_point_sampling(odd.cuda(), 300).cpu(), orc.furthest_point_sampling(odd, 300))
+    flat = cloud(12, 1, 5000)
+    flat[..., 2] = 0.5                                                           # zero extent along one axis
+    assert torch.equal(ext.furthest_point_sampling(flat.cuda(), 256).cpu(), orc.furthest_point_sampling(flat, 256))
+
+
+def test_fps_bucketed_equals_cluster_kernel_full_size(ext, monkeypatch):
+    x = scene_xyz([6, 7]).cuda()
+    monkeypatch.setenv("PN2_FPS_BUCKET_MIN", "1000000000")
+    a = ext.furthest_point_sampling(x, 2048)
+    monkeypatch.setenv("PN2_FPS_BUCKET_MIN", "1")
+    assert torch.equal(ext.furthest_point_sampling(x, 2048), a)
+    from situation3d_b200 import fused
+    inds, new_xyz = fused.fps_with_xyz(x, 2048)
+    assert torch.equal(inds, a)
+    assert torch.equal(new_xyz, torch.gather(x, 1, a.long()[..., None].expand(-1, -1, 3)))
 
 
 def test_fps_full_scene_vs_oracle(ext):
