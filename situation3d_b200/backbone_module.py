@@ -63,22 +63,45 @@ class Pointnet2Backbone(nn.Module):
         for m in (self.sa1, self.sa2, self.sa3, self.sa4, self.fp1, self.fp2):
             m.precision = precision
 
+    # ---- compact transport format ------------------------------------------------------------
+    def feature_row_elems(self):
+        """bf16 elements per feature row of the compact input format: the features sit at elements 3 .. 3+C-1, as in
+        an fp32 ``point_clouds`` row (elements 0..2 are zero), padded to whole 16-byte pieces."""
+        return (3 + self.input_feature_dim + 7) // 8 * 8
+
+    def pack_point_clouds(self, point_clouds):
+        """(B, N, 3+C) f32 -> (xyz (B,N,3) f32, feature rows (B,N,row_elems) bf16): the format a data loader ships when
+        host-to-device bandwidth bounds the step (half the bytes).  Works on CPU (pinned staging) and CUDA tensors;
+        round-to-nearest-even, the same conversion the bf16 arm applies on the device."""
+        C, R = self.input_feature_dim, self.feature_row_elems()
+        xyz = point_clouds[..., :3].contiguous()
+        rows = torch.zeros(point_clouds.shape[:2] + (R,), dtype=torch.bfloat16, device=point_clouds.device)
+        rows[..., 3:3 + C] = point_clouds[..., 3:3 + C].to(torch.bfloat16)
+        return xyz, rows
+
     # ---- fused eval path -------------------------------------------------------------------
     def _fused_images(self, pc):
-        if not (self.fused and pc.is_cuda and pc.dtype == torch.float32 and pc.size(-1) > 3):
+        if not (self.fused and pc.is_cuda and pc.dtype == torch.float32 and (pc.size(-1) > 3 or self.input_feature_dim > 0)):
             return None
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
         imgs = [m._fused_image(pc) for m in sas] + [m._fused_image(pc) for m in (self.fp1, self.fp2)]
         return None if any(i is None for i in imgs) else imgs
 
-    def _forward_fused(self, pc, imgs, data_dict):
-        B, N, W = pc.shape
-        pc = pc.contiguous()
-        dev = pc.device
+    def _forward_fused(self, pc, imgs, data_dict, xyz_in=None, rows_bf16=None):
+        """``pc`` (B, N, 3+C) f32, or -- the compact transport format of ``pack_point_clouds`` -- ``xyz_in`` (B, N, 3)
+        f32 plus ``rows_bf16`` (B, N, row_elems) bf16 feature rows."""
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
-        # the contiguous (B, N, 3) coordinates are written by the first sampling kernel itself while it loads the
-        # points out of point_clouds (no separate copy kernel); everything that reads them runs after that kernel
-        xyz = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        if pc is not None:
+            B, N, W = pc.shape
+            pc = pc.contiguous()
+            dev = pc.device
+            # the contiguous (B, N, 3) coordinates are written by the first sampling kernel itself while it loads the
+            # points out of point_clouds (no separate copy kernel); everything that reads them runs after that kernel
+            xyz = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        else:
+            B, N, _ = xyz_in.shape
+            xyz, dev = xyz_in.contiguous(), xyz_in.device
+            rows_bf16 = rows_bf16.contiguous()
         main = torch.cuda.current_stream(dev)
         # one sampling stream per caller stream: callers that keep several batches in flight (one stream
         # per batch) get independent sampling pyramids that overlap with each other's MLP kernels
@@ -97,7 +120,7 @@ class Pointnet2Backbone(nn.Module):
         with torch.cuda.stream(side):
             src = xyz
             for lvl, m in enumerate(sas):
-                if lvl == 0:
+                if lvl == 0 and pc is not None:
                     _fused.fps_rows_into(pc, inds[0], cxyz[0], xyz)
                 else:
                     _fused.fps_into(src, inds[lvl], cxyz[lvl])
@@ -105,7 +128,10 @@ class Pointnet2Backbone(nn.Module):
                 src = cxyz[lvl]
 
         feats, rows = [], []
-        src_xyz, table, ld, c, skip = xyz, pc[..., 3:], W, W - 3, 3
+        if pc is not None:
+            src_xyz, table, ld, c, skip = xyz, pc[..., 3:], W, W - 3, 3
+        else:
+            src_xyz, table, ld, c, skip = xyz, rows_bf16, rows_bf16.shape[2], self.input_feature_dim, 3
         for lvl, m in enumerate(sas):
             main.wait_event(ready[lvl])
             idx = _fused.ball_query(src_xyz, cxyz[lvl], m.radius, m.nsample)
@@ -131,6 +157,20 @@ class Pointnet2Backbone(nn.Module):
     def forward(self, data_dict):
         r"""Reads ``data_dict["point_clouds"]`` (B, N, 3 + input_feature_dim) and adds
         ``sa{1..4}_{xyz,features,inds}``, ``fp2_features`` (B,256,1024), ``fp2_xyz``, ``fp2_inds``."""
+        if "point_clouds" not in data_dict and "feature_rows_bf16" in data_dict:
+            # compact transport format (pack_point_clouds): fp32 coordinates + bf16 feature rows.  The bf16 arm rounds
+            # the features to bf16 as its first act anyway, so the results are bit-identical to the fp32 input's.
+            xyz_in, rows = data_dict["xyz"], data_dict["feature_rows_bf16"]
+            if self.training or self.precision != "bf16" or not self.fused:
+                raise RuntimeError("feature_rows_bf16 input is the eval-mode bf16 fused path only")
+            if not (xyz_in.is_cuda and xyz_in.dtype == torch.float32 and rows.dtype == torch.bfloat16 and
+                    rows.shape[2] == self.feature_row_elems()):
+                raise RuntimeError("xyz must be CUDA float32 (B,N,3) and feature_rows_bf16 CUDA bfloat16 (B,N,%d)"
+                                   % self.feature_row_elems())
+            imgs = self._fused_images(xyz_in)
+            if imgs is None or imgs[0].f32_only:
+                raise RuntimeError("the tensor-core path does not cover this configuration")
+            return self._forward_fused(None, imgs, data_dict, xyz_in, rows)
         pc = data_dict["point_clouds"]
         if not self.training and not (torch.is_grad_enabled() and pc.requires_grad):
             imgs = self._fused_images(pc)

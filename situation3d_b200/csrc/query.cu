@@ -375,12 +375,8 @@ extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
     nseg = min(nseg, max(1, ceil_div(n, kBqTile)));
     if (nseg < 1) return PN2_ERR_INVALID_ARGUMENT;   // nsample > ~1500: one segment's hit list exceeds shared memory
     const size_t smem = per_seg * nseg;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PN2_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          220 * 1024));
-        attr_set = true;
-    }
+    // per launch: the attribute belongs to the current device (one process may drive several GPUs)
+    PN2_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     const float radius2 = radius * radius;   // ball_query_gpu.cu:22, fp32 product
     dim3 grid(ceil_div(m, kBqCentres), b);
     ball_query_kernel<<<grid, nseg * 32, smem, as_stream(stream)>>>(n, m, radius2, nsample, nseg, new_xyz,
@@ -421,11 +417,7 @@ extern "C" int pn2_ball_query_ws(int b, int n, int m, float radius, int nsample,
     bq_grid_bin_kernel<<<pgrid, 256, 0, s>>>(n, 0, xyz, params, cursor, sorted);
     bq_grid_scan_kernel<<<b, 1024, 0, s>>>(params, cursor, start);
     bq_grid_bin_kernel<<<pgrid, 256, 0, s>>>(n, 1, xyz, params, cursor, sorted);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PN2_CUDA_TRY(cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
+    PN2_CUDA_TRY(cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     dim3 qgrid(ceil_div(m, warps), b);
     bq_grid_query_kernel<<<qgrid, warps * 32, per_warp * warps, s>>>(n, m, radius * radius, nsample, wpl, warps, new_xyz,
                                                                     params, start, sorted, idx);

@@ -9,7 +9,7 @@ import ctypes
 import torch
 import torch.nn as nn
 
-from ._lib import check, int_array, lib, ptr, ptr_array, stream_ptr
+from ._lib import Pn2Error, check, int_array, lib, ptr, ptr_array, stream_ptr
 
 
 def fold_shared_mlp(mlp):
@@ -320,14 +320,19 @@ def sa_bf16_table(img, table, ld, c, B, N, npoint, nsample, raw_skip=0):
                 if pair is not None:
                     table = lin_rows(pair[0], table, ctypes.c_void_p(base), B * N, kin, c1, False, ld).view(B, N, c1)
         if pair is None:
+            bf16_skip = raw_skip if table.dtype == torch.bfloat16 else 0
             if table.dtype != torch.bfloat16:
                 table = bf16_rows(table, ld, c)
             kin = table.shape[2]
-            pair = img.split(kin, 0, True)
+            # bf16 rows may carry `raw_skip` unused leading elements (the compact transport format keeps every feature
+            # in the column it has in the fp32 row, so both formats feed the tensor cores identical operands)
+            pair = img.split(kin, bf16_skip, True)
             if pair is not None:
                 table = lin_rows(pair[0], table, ptr(table), B * N, kin, c1, True, kin).view(B, N, c1)
         if pair is not None:
             return table, pair[1], c1
+    if table.dtype == torch.bfloat16 and raw_skip:
+        raise Pn2Error("bf16 feature rows with leading padding need the split first layer (csrc/lin_tc.cu)")
     if table.dtype != torch.bfloat16:
         table = bf16_rows(table, ld, c)
     return table, img.image, c
@@ -349,6 +354,20 @@ def sa_bf16_fused(dims, image, c_eff, xyz, new_xyz, idx, table, inv_radius, want
     return out, out_rows
 
 
+def _f32_alternative(img):
+    """fp32 image of a stack the tensor-core kernels do not cover for this call's shape; raises (instead of handing a
+    NULL image to the C ABI) when the fp32 kernel does not cover it either."""
+    alt = img if img.f32_only else img._f32_alt
+    if alt is None:
+        alt = MlpImage()
+        alt.dims, alt.folded, alt.image = img.dims, img.folded, _pack_f32(img.dims, img.folded)
+        img._f32_alt = alt
+    if alt.image is None:
+        raise Pn2Error("no fused kernel covers the SharedMLP %s with this layer shape; construct the module with "
+                       "fused=False" % (img.dims,))
+    return alt
+
+
 def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, want_rows=True, raw_skip=0):
     """Fused SA layer on tcgen05 (pn2_sa_tc_forward).  ``table`` is either f32 channel-last rows (read in place by
     the per-point GEMM, or packed to bf16 here) or the bf16 row table a previous layer produced.  Shapes the
@@ -359,11 +378,7 @@ def sa_forward_bf16(img, xyz, new_xyz, idx, table, ld, c, use_xyz, inv_radius, w
     ok = use_xyz and not img.f32_only and len(dims) == 4 and \
         lib.pn2_sa_tc_supported(c, dims[1], dims[2], dims[3], npoint, nsample)
     if not ok:
-        alt = img if img.f32_only else img._f32_alt
-        if alt is None:
-            alt = MlpImage()
-            alt.dims, alt.folded, alt.image = img.dims, img.folded, _pack_f32(img.dims, img.folded)
-            img._f32_alt = alt
+        alt = _f32_alternative(img)
         rows = _f32_rows(table)
         if rows is not table:
             ld = rows.shape[2]
@@ -385,11 +400,7 @@ def fp_forward_bf16(img, dist2, idx, known_rows, skip_rows, want_rows=True):
     dims = img.dims
     ok = not img.f32_only and len(dims) == 3 and lib.pn2_fp_tc_supported(c_known, c_skip, dims[1], dims[2])
     if not ok:
-        alt = img if img.f32_only else img._f32_alt
-        if alt is None:
-            alt = MlpImage()
-            alt.dims, alt.folded, alt.image = img.dims, img.folded, _pack_f32(img.dims, img.folded)
-            img._f32_alt = alt
+        alt = _f32_alternative(img)
         return fp_forward_f32(alt, dist2, idx, _f32_rows(known_rows), _f32_rows(skip_rows), want_rows)
     known_rows, skip_rows = _bf16_rows(known_rows).contiguous(), _bf16_rows(skip_rows)
     cout = dims[2]

@@ -16,31 +16,46 @@ images of the fused layers: capture again after the module's parameters change.
 import torch
 
 
+def _as_inputs(example):
+    """A (B,N,3+C) f32 tensor -> {"point_clouds": t}; an (xyz f32, feature rows bf16) pair -- the compact transport
+    format of ``Pointnet2Backbone.pack_point_clouds`` -- -> {"xyz": ..., "feature_rows_bf16": ...}; dicts pass."""
+    if isinstance(example, dict):
+        return dict(example)
+    if isinstance(example, (tuple, list)):
+        return {"xyz": example[0], "feature_rows_bf16": example[1]}
+    return {"point_clouds": example}
+
+
 class GraphedBackbone:
     def __init__(self, net, example, stream=None, static_input=None, warmup=2):
         assert not net.training, "the fused (forward-only) path is what gets captured"
         self.net = net
-        self.stream = stream if stream is not None else torch.cuda.Stream(device=example.device)
-        self.static_in = static_input if static_input is not None else torch.empty_like(example)
+        example = _as_inputs(example)
+        first = next(iter(example.values()))
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=first.device)
+        self.static_in = _as_inputs(static_input) if static_input is not None else {k: torch.empty_like(v) for k, v in example.items()}
         from ._lib import lib
         with torch.no_grad():
             with torch.cuda.stream(self.stream):
                 if static_input is None:
-                    self.static_in.copy_(example)
+                    for k, v in example.items():
+                        self.static_in[k].copy_(v)
                 for _ in range(max(1, warmup)):          # weight images, allocator blocks, side stream: all warm
-                    net({"point_clouds": self.static_in})
+                    net(dict(self.static_in))
             self.stream.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             n0 = lib.pn2_launch_count()
             with torch.cuda.graph(self.graph, stream=self.stream):
-                self.out = net({"point_clouds": self.static_in})
+                self.out = net(dict(self.static_in))
             self.launches_per_replay = int(lib.pn2_launch_count() - n0)   # kernels of this library inside the graph
 
     def __call__(self, pc=None):
         """Enqueue one step on ``self.stream`` (after copying ``pc`` into the static input when given)."""
         with torch.cuda.stream(self.stream):
-            if pc is not None and pc.data_ptr() != self.static_in.data_ptr():
-                self.static_in.copy_(pc, non_blocking=True)
+            if pc is not None:
+                for k, v in _as_inputs(pc).items():
+                    if v.data_ptr() != self.static_in[k].data_ptr():
+                        self.static_in[k].copy_(v, non_blocking=True)
             self.graph.replay()
         return self.out
 
@@ -54,22 +69,29 @@ class BackbonePipeline:
             ...
             out = pipe.result(ticket)                           # dict of pinned host tensors (waits for that batch only)
 
+    ``example`` / ``submit`` take either the reference's (B, N, 3+C) f32 ``point_clouds`` or the compact pair
+    ``net.pack_point_clouds(point_clouds)`` = (xyz f32, feature rows bf16): the step is bound by the host-to-device
+    copy, the bf16 arm rounds the features to bf16 first thing anyway, so shipping them as bf16 halves the bytes and
+    gives bit-identical results (tests/test_fused_gpu.py::test_compact_input_is_bit_identical).
+
     A lane is reused round robin: ``submit`` first waits for the lane's previous batch, so at most ``lanes`` batches
     are in flight and a ticket's host buffers stay valid until ``lanes`` further submissions.
     """
 
     def __init__(self, net, example, lanes=8, outputs=("fp2_features", "fp2_xyz", "fp2_inds"), streams=None):
-        dev = example.device if example.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        example = example.to(dev)
+        example = _as_inputs(example)
+        first = next(iter(example.values()))
+        dev = first.device if first.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        example = {k: v.to(dev) for k, v in example.items()}
         self.streams = list(streams) if streams is not None else [torch.cuda.Stream(device=dev) for _ in range(lanes)]
-        self.inputs = [example.clone() for _ in self.streams]
+        self.inputs = [{k: v.clone() for k, v in example.items()} for _ in self.streams]
         self.steps = [GraphedBackbone(net, example, stream=st, static_input=buf) for st, buf in zip(self.streams, self.inputs)]
         self.outputs = tuple(outputs)
         self.host = [{k: torch.empty_like(s.out[k], device="cpu").pin_memory() for k in self.outputs} for s in self.steps]
         self.done = [torch.cuda.Event() for _ in self.streams]
         self._busy = [False] * len(self.streams)
         self._next = 0
-        self.h2d_bytes = example.numel() * example.element_size()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in example.values())
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.host[0].values())
 
     def submit(self, pc):
@@ -78,7 +100,8 @@ class BackbonePipeline:
         if self._busy[ln]:
             self.done[ln].synchronize()
         with torch.cuda.stream(self.streams[ln]):
-            self.inputs[ln].copy_(pc, non_blocking=True)
+            for k, v in _as_inputs(pc).items():
+                self.inputs[ln][k].copy_(v, non_blocking=True)
             out = self.steps[ln]()
             for k, v in self.host[ln].items():
                 v.copy_(out[k], non_blocking=True)

@@ -36,6 +36,12 @@ def _inference_only(module, *tensors):
     return not any(t is not None and t.requires_grad for t in tensors)
 
 
+def _all_f32(*tensors):
+    """The fused kernels read raw float32 pointers; anything else (half / double after net.half(), autocast) takes the
+    unfused path, whose ``_ext`` wrappers raise like the reference's CHECK_IS_FLOAT (utils.h:19-25)."""
+    return all(t is None or t.dtype == torch.float32 for t in tensors)
+
+
 def _max_over_samples(x):
     # (B, C, npoint, nsample) -> (B, C, npoint)
     return F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
@@ -141,7 +147,7 @@ class PointnetSAModuleVotes(nn.Module):
 
     # ---- fused eval path ---------------------------------------------------------------
     def _fused_image(self, xyz, features=None):
-        ok = self.fused and xyz.is_cuda and _inference_only(self, xyz, features)
+        ok = self.fused and xyz.is_cuda and _all_f32(xyz, features) and _inference_only(self, xyz, features)
         if not ok or self.npoint is None or self.pooling != 'max' or self.sample_uniformly:
             return None
         img = self._image.get(self.mlp_module, self.precision)
@@ -228,7 +234,7 @@ class PointnetFPModule(nn.Module):
         self._image = _fused.MlpImage()
 
     def _fused_image(self, ref, *feats):
-        if not (self.fused and ref.is_cuda and _inference_only(self, *feats)):
+        if not (self.fused and ref.is_cuda and _all_f32(ref, *feats) and _inference_only(self, *feats)):
             return None
         img = self._image.get(self.mlp, self.precision, kind="fp")
         return img if img is not None and img.image is not None else None

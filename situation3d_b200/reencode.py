@@ -88,12 +88,42 @@ class SituationReencoder(nn.Module):
         self.sigma = sigma
         self.to_agent_frame = to_agent_frame
 
+    def _forward_autograd(self, tokens, positions, situation):
+        """Differentiable twin of pn2_reencode_forward (temp.py:42-97 transform, sqa_module.py:274-278,319-321 embedding
+        + add, :328-336 prior) in plain PyTorch ops."""
+        if positions.size(-1) == 2:
+            positions = torch.cat([positions, torch.zeros_like(positions[..., :1])], dim=-1)
+        t, q = situation[:, :3], situation[:, 3:]
+        x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R = torch.stack([x * x - y * y - z * z + w * w, 2 * (x * y - z * w), 2 * (x * z + y * w),
+                         2 * (x * y + z * w), -x * x + y * y - z * z + w * w, 2 * (y * z - x * w),
+                         2 * (x * z - y * w), 2 * (y * z + x * w), -x * x - y * y + z * z + w * w], dim=1).view(-1, 3, 3)
+        if self.to_agent_frame:
+            new_pos = torch.matmul(positions - t[:, None, :], R)                # R^T (p - t)
+        else:
+            new_pos = torch.matmul(positions, R.transpose(1, 2)) + t[:, None, :]   # R p + t
+        out = tokens + self.pos_embed(new_pos[..., :2])
+        d2 = (positions[..., :2] - t[:, None, :2]).pow(2).sum(-1)
+        prior = torch.exp(-d2 / (2 * self.sigma ** 2))
+        prior = prior / prior.sum(dim=1, keepdim=True)
+        return out, new_pos, prior
+
     def forward(self, data_dict):
         """Reads ``scene_feat`` (B,T,D) [falls back to ``att_feat_pre``], ``scene_positions`` (B,T,3|2)
         and ``auxiliary_task`` (B,7); writes ``att_feat_pre`` (input tokens), ``scene_feat`` (re-encoded),
         ``scene_positions_agent`` and ``auxiliary_task_loc_gt`` (the prior), the names SIG3D.forward uses
         (sqa_module.py:316-336)."""
         tokens = data_dict["scene_feat"] if "scene_feat" in data_dict else data_dict["att_feat_pre"]
+        needs_grad = torch.is_grad_enabled() and (tokens.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.training or needs_grad:
+            # the fused kernel is forward-only: training (or any caller that differentiates) runs the same statements
+            # as PyTorch ops so that pos_embed, the tokens and everything upstream receive gradients
+            out, new_pos, prior = self._forward_autograd(tokens, data_dict["scene_positions"], data_dict["auxiliary_task"])
+            data_dict["att_feat_pre"] = tokens
+            data_dict["scene_feat"] = out
+            data_dict["scene_positions_agent"] = new_pos
+            data_dict["auxiliary_task_loc_gt"] = prior
+            return data_dict
         out, new_pos, prior = reencode_tokens(
             tokens, data_dict["scene_positions"], data_dict["auxiliary_task"],
             self.pos_embed[0].weight, self.pos_embed[0].bias, self.pos_embed[2].weight, self.pos_embed[2].bias,

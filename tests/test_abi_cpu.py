@@ -39,7 +39,9 @@ def test_library_basics_without_gpu():
     assert _lib.lib.pn2_mlp_f32_image_bytes(3, dims) == 4 * (132 * 64 + 64 + 64 * 64 + 64 + 64 * 128 + 128)
     assert _lib.lib.pn2_mlp_f32_supported(3, dims) == 1
     assert _lib.lib.pn2_mlp_f32_supported(2, _lib.int_array([4096, 4096, 64])) == 0
-    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 40000, 2048) == 0
+    # large scenes: the bucketed kernel's scratch, per scene 20 bytes per (padded) point + 2 per point, 256-byte aligned
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 40000, 2048) == 8 * ((20 * 40000 + 2 * 40000 + 255) // 256 * 256)
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 2048, 1024) == 0    # small scenes: register-resident
     # argument validation happens before any CUDA call
     assert _lib.lib.pn2_gather_points(-1, 1, 1, 1, None, None, None, None) == -1
     assert _lib.lib.pn2_ball_query(1, 10, 4, 0.5, 8, None, None, None, None) == -1
@@ -218,3 +220,27 @@ def test_voxel_pe_and_projection_reject_cpu_tensors():
     from situation3d_b200.projection import ProjectionHelper
     with pytest.raises(RuntimeError):
         ProjectionHelper(torch.eye(4), 0.4, 4.0, [41, 32], 0.05, cuda=False)
+
+
+def test_reencoder_training_path_matches_oracle_and_differentiates():
+    """SituationReencoder in train mode (or whenever gradients are needed) runs the PyTorch twin of the fused kernel:
+    same numbers as the oracle, and pos_embed / tokens receive gradients (the fused kernel is forward-only)."""
+    import torch
+    from oracle import pn2_oracle as orc
+    from situation3d_b200.reencode import SituationReencoder
+    from situation3d_b200.synthetic import make_situations
+    torch.manual_seed(0)
+    for agent in (False, True):
+        re = SituationReencoder(to_agent_frame=agent).train()
+        tokens = torch.randn(3, 40, 256, requires_grad=True)
+        pos = torch.randn(3, 40, 3)
+        sit = torch.from_numpy(make_situations(3))
+        d = re({"scene_feat": tokens, "scene_positions": pos, "auxiliary_task": sit})
+        pe = re.pos_embed
+        want_tok, want_pos, want_prior = orc.reencode(tokens.detach(), pos, sit, pe[0].weight.detach(), pe[0].bias.detach(),
+                                                      pe[2].weight.detach(), pe[2].bias.detach(), to_agent_frame=agent)
+        torch.testing.assert_close(d["scene_feat"], want_tok, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(d["scene_positions_agent"], want_pos, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(d["auxiliary_task_loc_gt"], want_prior, rtol=1e-4, atol=1e-8)
+        d["scene_feat"].square().mean().backward()
+        assert tokens.grad is not None and pe[0].weight.grad is not None and pe[2].weight.grad.abs().sum() > 0

@@ -489,6 +489,39 @@ def test_backbone_pipeline_from_host_buffers():
         pipe.drain()
 
 
+def test_compact_input_is_bit_identical():
+    """fp32 coordinates + bf16 feature rows (Pointnet2Backbone.pack_point_clouds: half the host-to-device bytes) give
+    bit-identical results to the reference's fp32 point_clouds on the bf16 arm, eagerly and through the pipeline from
+    pinned host buffers; the format is refused where it would change results (fp32 arm, training)."""
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.graphs import BackbonePipeline
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=129, precision="bf16")).eval().cuda()
+    host = [torch.from_numpy(make_batch(2, 40000, 129, first_seed=s)) for s in (21, 22, 23)]
+    keys = ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds", "fp2_xyz", "fp2_features", "sa1_features",
+            "sa2_features", "sa4_features")
+    with torch.no_grad():
+        want = [{k: net({"point_clouds": h.cuda()})[k].cpu() for k in keys} for h in host]
+        packed = [net.pack_point_clouds(h) for h in host]                      # on the host, like a data loader would
+        assert packed[0][1].dtype == torch.bfloat16 and packed[0][1].shape == (2, 40000, 136)
+        for (xyz, rows), w in zip(packed, want):
+            out = net({"xyz": xyz.cuda(), "feature_rows_bf16": rows.cuda()})
+            for k in keys:
+                assert torch.equal(out[k].cpu(), w[k]), k
+        pinned = [(x.pin_memory(), r.pin_memory()) for x, r in packed]
+        pipe = BackbonePipeline(net, (pinned[0][0].cuda(), pinned[0][1].cuda()), lanes=2)
+        assert pipe.h2d_bytes == 2 * 40000 * (12 + 136 * 2)
+        for j, pr in enumerate(pinned):
+            got = pipe.result(pipe.submit(pr))
+            for k in ("fp2_features", "fp2_xyz", "fp2_inds"):
+                assert torch.equal(got[k], want[j][k]), (j, k)
+        pipe.drain()
+        f32 = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=129, precision="fp32")).eval().cuda()
+        with pytest.raises(RuntimeError):
+            f32({"xyz": packed[0][0].cuda(), "feature_rows_bf16": packed[0][1].cuda()})
+
+
 @pytest.mark.parametrize("name", ["rand", "sin"])
 def test_voxel_pe_vs_reference_statements(name):
     """csrc/voxel_pe.cu against the outputs of the reference's own statements (blip2_t5.py:107-118 and

@@ -324,3 +324,39 @@ def test_projection_oracle_vs_reference_class():
     for v in range(nviews):
         s = orc.project(g["label"][v], g["indices_3d"][v], g["indices_2d"][v], n).astype(np.float64).sum()
         assert abs(s - g["project_checksum"][v]) <= 1e-9 * max(1.0, abs(g["project_checksum"][v]))
+
+
+# ---- pinned to the reference's own Python modules, executed (not goldens) ---------------------------------------
+
+def test_backbone_wiring_equals_reference_modules_byte_code():
+    """oracle/ref_modules.py: the reference's unmodified pointnet2_modules / pointnet2_utils / pytorch_utils (byte code
+    compiled from /root/reference into oracle/_ref/) composed as Pointnet2Backbone over the oracle's operators give
+    exactly what the oracle's restated wiring (orc.backbone) gives, from the same state_dict."""
+    import types
+    from oracle import ref_modules, workload
+    ref_modules.build()
+    if not ref_modules.available():
+        pytest.skip("oracle/_ref/*.pyc not built (needs /root/reference once)")
+    ext = types.ModuleType("pn2_oracle_ext")
+    for name in ("gather_points", "gather_points_grad", "furthest_point_sampling", "three_nn", "three_interpolate",
+                 "three_interpolate_grad", "ball_query", "group_points", "group_points_grad"):
+        setattr(ext, name, getattr(orc, name))
+    net = ref_modules.make_backbone(ref_modules.load(ext), 9).eval()
+    sd = workload.backbone_state_dict(9, seed=3)
+    assert not net.load_state_dict(sd).missing_keys
+    pc = T(workload.synthetic().make_batch(2, 3000, 9))
+    with torch.no_grad():
+        got, want = net(pc), orc.backbone(pc, sd)
+    for k in ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds", "fp2_xyz", "fp2_features", "sa2_features"):
+        assert torch.equal(got[k], want[k]), k
+
+
+def test_reference_arm_workload_does_not_import_the_product():
+    """bench.py --impl reference builds its scenes and weights through oracle/workload.py only."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from oracle import workload; workload.synthetic().make_scene(0, 64, 3); "
+            "workload.backbone_state_dict(); assert not any(m.startswith('situation3d_b200') for m in sys.modules), "
+            "[m for m in sys.modules if m.startswith('situation3d')]") % __import__("os").path.dirname(
+        __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    subprocess.check_call([sys.executable, "-c", code])
