@@ -61,6 +61,9 @@ CONFIGS = {
             what="config 5: stress, 200 000-point scenes, SA npoint 4096/2048/1024/512, nsample 64/32/16/16, "
                  "8 scenes/GPU (64 scenes over 8 GPUs)"),
 }
+CONFIGS[4] = dict(batch=8, points=40000, precision="fp32", lanes=1, npoints=(2048, 1024, 512, 256), train=True,
+                  what="config 4: SQA3D-shaped training step, backbone forward + backward (train-mode BatchNorm, loss = "
+                       "mean(fp2_features^2)), SGD, gradient all-reduce over NCCL overlapped with backward, 8 scenes/GPU")
 RADII, NSAMPLES = (0.2, 0.4, 0.8, 1.2), (64, 32, 16, 16)
 INDEX_KEYS = ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds")
 
@@ -71,7 +74,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--precision", default=None, help="override the configuration's arm: fp32 | bf16")
     ap.add_argument("--batch", type=int, default=None, help="override scenes per GPU per step")
     ap.add_argument("--points", type=int, default=None, help="override points per scene")
@@ -338,7 +341,7 @@ def ncu_traffic():
 
 def reference_cuda_arm(pc, sd, ours, steps=24, lanes=8):
     """The existing GPU implementation on the same B200: the reference's own CUDA kernels (oracle/_ref/pn2_ref_ext.so,
-    unmodified sources) driven by the reference's own unmodified Python modules (oracle/_ref/*.pyc, byte code of
+    unmodified sources) driven by the reference's own unmodified Python modules (oracle/_ref/*.bytecode, byte code of
     lib/pointnet2/{pointnet2_modules,pointnet2_utils,pytorch_utils}.py) with stock PyTorch conv / BN / ReLU / max-pool
     (cuDNN, TF32 allowed as by torch's default), composed as Pointnet2Backbone (oracle/ref_modules.py), `lanes` batches
     in flight on separate streams like this library's arm.  Also compares its outputs with `ours` on the same batch."""
@@ -637,9 +640,90 @@ class Runner:
         return rec
 
 
+def train_config(args, rank, local_rank, world, K):
+    """BASELINE.json config 4: the training step (situation3d_b200.train_step.BackboneTrainer) at 8 scenes per GPU."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.synthetic import make_batch
+    from situation3d_b200.train_step import BackboneTrainer
+    cfg = config_of(args, 4)
+    dev = torch.device("cuda", local_rank)
+    B = cfg["batch"]
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True            # the reference's cuDNN convolutions run TF32 by torch's default
+    torch.manual_seed(0)
+    net = Pointnet2Backbone(input_feature_dim=129).to(dev)
+    # parity of the row-layout training path against the reference wiring (same parameters, 2 scenes, strict fp32)
+    par = None
+    if not args.no_parity:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        a, b = copy.deepcopy(net).train(), copy.deepcopy(net).train()
+        b.train_layout = "reference"
+        pc2 = torch.from_numpy(make_batch(2, cfg["points"], 129, first_seed=rank * B)).to(dev)
+        la = a({"point_clouds": pc2})["fp2_features"].square().mean()
+        lb = b({"point_clouds": pc2})["fp2_features"].square().mean()
+        la.backward()
+        lb.backward()
+        worst = max(float((p1.grad - p2.grad).abs().max()) / (float(p2.grad.abs().max()) + 1e-12)
+                    for p1, p2 in zip(a.parameters(), b.parameters()))
+        rel = abs(float(la) - float(lb)) / max(abs(float(lb)), 1e-30)
+        par = {"against": "the reference's operator-by-operator wiring (QueryAndGroup -> NCHW SharedMLP -> max_pool2d) with "
+                          "autograd through the *_grad kernels, same parameters, 2 scenes, fp32 without TF32",
+               "loss_rel_diff": rel, "max_grad_diff_over_max_grad": worst, "ok": bool(rel <= 1e-4 and worst <= 5e-3)}
+        del a, b, pc2
+        torch.cuda.empty_cache()
+        torch.backends.cuda.matmul.allow_tf32 = True
+    tr = BackboneTrainer(net)
+    pc = torch.from_numpy(make_batch(B, cfg["points"], 129, first_seed=rank * B)).to(dev)
+    for _ in range(3):
+        tr.step(pc)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(K):
+        loss = tr.step(pc)
+    e.record()
+    torch.cuda.synchronize()
+    dt = s.elapsed_time(e) * 1e-3
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    ar_us = None
+    if world > 1:
+        t = torch.zeros_like(tr.bucket.flat)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(20):
+            dist.all_reduce(t)
+        e.record()
+        torch.cuda.synchronize()
+        ar_us = 1e3 * s.elapsed_time(e) / 20
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    rec = {"config": 4, "workload": cfg["what"], "scenes_per_gpu": B, "points": cfg["points"], "steps": K,
+           "value": world * B * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K, "loss": float(loss),
+           "layout": "channel-last rows (train_rows.py); GEMMs by cuBLAS with TF32 allowed, indices by libpn2_b200",
+           "grad_bytes": tr.bucket.flat.numel() * 4, "allreduce_us_alone": ar_us,
+           "allreduce": "3 chunks launched from gradient hooks during backward (sharding.FlatGradAllReduce.enable_overlap)"
+                        if world > 1 else None,
+           "parity": par}
+    if par is not None:
+        par["all_ranks_ok"] = par["ok"]
+    del tr, net, pc
+    torch.cuda.empty_cache()
+    return [rec]
+
+
 def sub_config(args, which, rank, local_rank, world, K):
     """A short run of another BASELINE.json configuration: resident throughput + the parity gate."""
     import torch
+    if which == 4:
+        return train_config(args, rank, local_rank, world, K)
     recs = []
     sizes = (100000, 150000, 200000) if which == 5 else (None,)
     for n in sizes:
@@ -669,6 +753,17 @@ def run_ours(args, rank, local_rank, world):
     prev_affinity, numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else (None, 0)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.config == 4:
+        rec = train_config(args, rank, local_rank, world, args.steps)[0]
+        if rank == 0:
+            line = {"metric": "Pointnet2Backbone training step scenes/sec (40k pts)", "value": rec["value"], "unit": UNIT,
+                    "n_gpus": world, "steps": args.steps, "warmup": 3, "ms_per_step": rec["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 GEMMs)",
+                    "data": "synthetic", "config": {"workload": rec["workload"], "config_id": 4}, "train": rec}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     cfg = config_of(args)
     if cfg["precision"] == "bf16" and "bf16" not in fused.SA_FORWARD:
         cfg["precision"] = "fp32"
@@ -761,7 +856,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- the other configurations, short ----
     subs = {}
     if not args.no_sub_configs and args.config == 2:
-        for which in (1, 3, 5):
+        for which in (1, 3, 4, 5):
             try:
                 subs[str(which)] = sub_config(args, which, rank, local_rank, world, max(4, min(K, 12)))
             except Exception as ex:

@@ -23,7 +23,8 @@ NAMES = ("pytorch_utils", "pointnet2_utils", "pointnet2_modules")
 
 
 def pyc_path(name):
-    return os.path.join(OUT_DIR, name + ".pyc")
+    # (not *.pyc: snapshot tools tend to drop those as caches)
+    return os.path.join(OUT_DIR, name + ".bytecode")
 
 
 def build():

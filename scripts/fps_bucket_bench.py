@@ -65,9 +65,11 @@ prof = torch.zeros(8, dtype=torch.int64, device="cuda")
 for _ in range(2):
     check(lib.pn2_debug_fps_bucket_profile(B, n, m, ptr(xyz), ptr(idx), ptr(prof), ptr(ws), nbytes, stream_ptr()), "prof")
 torch.cuda.synchronize()
-p = prof.cpu().numpy()[:5] / (m - 1)
-out["bucket_cycles_per_round"] = dict(zip(["tests", "updates", "thread_warp_argmax", "barrier", "table_argmax"], [float(round(v, 1)) for v in p]))
+pr = prof.cpu().numpy()
+p = pr[:6] / (m - m // 2)          # the kernel accumulates over rounds m/2 .. m-1 (steady state)
+out["bucket_cycles_per_round"] = dict(zip(["tests+publish", "barrier1+scan", "updates+own_argmax", "barrier2", "final_argmax+refresh"], [float(round(v, 1)) for v in p[:5]]))
 out["bucket_cycles_per_round"]["sum"] = float(round(p.sum(), 1))
+out["bucket_sources_per_warp_round"] = float(pr[6]) / (m - m // 2)
 # prologue cost: a launch with m = 1 does the binning only
 idx1 = torch.empty((B, 1), dtype=torch.int32, device="cuda")
 out["bucket_prologue_ms"] = timed(lambda: check(lib.pn2_furthest_point_sampling_xyz_ws(B, n, 1, ptr(xyz), ptr(idx1), None, ptr(ws), nbytes, stream_ptr()), "fps"))

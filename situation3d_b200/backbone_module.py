@@ -49,6 +49,9 @@ class Pointnet2Backbone(nn.Module):
                                          mlp=[256, 128, 128, 256], **kw)
         self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
         self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256], fused=fused, precision=precision)
+        # training-mode layout: "rows" = the same mathematics on channel-last rows (train_rows.py: row gathers, one GEMM
+        # per 1x1 convolution, BatchNorm over the row axis); "reference" = operator by operator as the reference wires it
+        self.train_layout = "rows"
         self._side_streams = {}
         self.sm_partition = None      # optional streams.SmPartition: sampling side streams come from its FPS group
 
@@ -176,6 +179,13 @@ class Pointnet2Backbone(nn.Module):
             imgs = self._fused_images(pc)
             if imgs is not None:
                 return self._forward_fused(pc, imgs, data_dict)
+
+        if self.training and self.train_layout == "rows" and pc.is_cuda and pc.dtype == torch.float32:
+            from . import train_rows
+            mods = (self.sa1, self.sa2, self.sa3, self.sa4)
+            if all(train_rows.rows_supported(m.mlp_module) and m.pooling == "max" and not m.sample_uniformly and
+                   not m.ret_unique_cnt for m in mods) and all(train_rows.rows_supported(m.mlp) for m in (self.fp1, self.fp2)):
+                return train_rows.backbone_forward_rows(self, pc, data_dict)
 
         xyz, features = self._break_up_pc(pc)
         for lvl, m in enumerate((self.sa1, self.sa2, self.sa3, self.sa4), start=1):

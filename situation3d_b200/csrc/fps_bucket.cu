@@ -113,20 +113,23 @@ __device__ __forceinline__ Cand warp_best(const Cand &c, int lg_bs, int cnt)
 }
 
 // PPL points per lane in a bucket (bucket = 32*PPL points), CH buckets per super-bucket, SS super-buckets per
-// thread; SDIST: running distances in shared memory (else in the workspace).
+// thread; SDIST: running distances in shared memory (else in the workspace).  The CTA starts with kBT threads for the
+// binning; the rounds run on the first `nwa` warps only (one thread per super-bucket), the others leave.
 template <int PPL, int CH, int SS, bool SDIST>
 __global__ void __launch_bounds__(kBT, 1)
 fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int pitch, int *__restrict__ idxs,
                   float *__restrict__ new_xyz, float *__restrict__ xyz_copy, unsigned char *__restrict__ ws,
-                  size_t ws_stride, int npad, long long *__restrict__ prof)
+                  size_t ws_stride, int npad, int nwa, long long *__restrict__ prof)
 {
+    static_assert(CH == 4, "the work-queue bitmaps hold four buckets per lane");
     constexpr int BS = 32 * PPL;
+    constexpr int kWords = SS * CH;                          // bitmap words per warp: one per (ss, c), bit = owner lane
     extern __shared__ __align__(16) unsigned char dyn[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(dyn);     // prologue: cell histogram / offsets
     __shared__ uint32_t red[kBW][8];
     __shared__ uint32_t wbase[kBW + 1];
-    __shared__ __align__(16) uint4 table[2][kBW];            // per round parity: (key, x, y, z) of every warp's winner
-    __shared__ uint32_t table_i[2][kBW];                     //                   its point index
+    __shared__ __align__(8) int2 tableA[kBW];                // per warp: best (distance bits, bucket) it accounts for this round
+    __shared__ __align__(16) uint32_t qmask[2][kBW * kWords];   // the round's work queue: which buckets can change (by round parity)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int scene = blockIdx.x;
@@ -138,6 +141,12 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     float4 *pts = reinterpret_cast<float4 *>(w);                                  // npad x (x, y, z, index)
     float *dist = SDIST ? reinterpret_cast<float *>(dyn) : reinterpret_cast<float *>(w + (size_t)16 * npad);
     unsigned short *cellid = reinterpret_cast<unsigned short *>(w + (size_t)20 * npad);
+    // per bucket, in shared memory (after the distances, or -- distances in the workspace -- over the dead histogram):
+    // (largest running distance, x, y, z of that candidate) and the candidate's point index
+    const int nbcap = npad / BS;
+    unsigned char *mbase = dyn + (SDIST ? (size_t)npad * 4 : 0);
+    float4 *meta4 = reinterpret_cast<float4 *>(mbase);
+    uint32_t *cidx = reinterpret_cast<uint32_t *>(mbase + (size_t)16 * nbcap);
 
     for (int i = tid; i < kCells; i += kBT) hist[i] = 0u;
 
@@ -239,15 +248,18 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
             pts[pos] = make_float4(src[(size_t)sp * k], src[(size_t)sp * k + 1], src[(size_t)sp * k + 2], __int_as_float(k));
         }
     }
-    __syncthreads();                                     // histogram dead from here: `dist` may alias it
+    __syncthreads();                                     // histogram dead from here: `dist` / the bucket records may alias it
+    const int NW = nwa;                                  // warps that run the rounds
+    if (warp >= NW) return;
+    const int nthr = NW * 32;
+#define PN2_FPSB_BAR() asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory")
 
-    // ---- P5: running distances, bucket boxes and first candidates into registers ----------------------------
-    // bucket (ss, l, c) of warp w = global bucket (((ss*32 + l)*kBW + w)*CH + c): neighbouring super-buckets
-    // belong to different warps, so the few active ones of a round spread over the warps
+    // ---- P5: running distances, bucket boxes (registers of the owner thread) and first candidates (shared memory) ----
+    // super-bucket (ss, l) of warp w = global super-bucket (ss*32 + l)*NW + w: neighbouring super-buckets belong to
+    // different warps; its CH buckets are consecutive.  A running distance lives as a float; comparisons of maxima use
+    // its bit pattern as a SIGNED integer (non-negative floats order like integers; -1.0 = "no candidate" is negative).
     float slo[SS][3], shi[SS][3], smax[SS];
     float clo[SS][CH][3], chi[SS][CH][3], cmx[SS][CH];
-    uint32_t cki[SS][CH];
-    float ccx[SS][CH], ccy[SS][CH], ccz[SS][CH];
 #pragma unroll
     for (int ss = 0; ss < SS; ++ss) {
         smax[ss] = -1.f;
@@ -255,7 +267,7 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
         for (int a = 0; a < 3; ++a) { slo[ss][a] = INFINITY; shi[ss][a] = -INFINITY; }
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-            cmx[ss][c] = -1.f; cki[ss][c] = 0u; ccx[ss][c] = ccy[ss][c] = ccz[ss][c] = 0.f;
+            cmx[ss][c] = -1.f;
 #pragma unroll
             for (int a = 0; a < 3; ++a) { clo[ss][c][a] = INFINITY; chi[ss][c][a] = -INFINITY; }
         }
@@ -263,11 +275,11 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
 #pragma unroll
     for (int ss = 0; ss < SS; ++ss) {
         for (int l = 0; l < 32; ++l) {
-            const long long sup = (long long)(ss * 32 + l) * kBW + warp;
+            const long long sup = (long long)(ss * 32 + l) * NW + warp;
             if (sup * CH * BS >= nv) break;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const long long base = (sup * CH + c) * BS;
+                const long long bkt = sup * CH + c, base = bkt * BS;
                 if (base >= nv) continue;
                 Cand best; best.key = 0u; best.idx = 0u; best.x = best.y = best.z = 0.f;
                 float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -293,8 +305,9 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
                     rl[a] = ord_inv(__reduce_min_sync(kFullMask, ord_key(bl[a])));
                     rh[a] = ord_inv(__reduce_max_sync(kFullMask, ord_key(bh[a])));
                 }
+                if (lane == 0) { meta4[bkt] = make_float4(key_dist(wb.key), wb.x, wb.y, wb.z); cidx[bkt] = wb.idx; }
                 if (lane == l) {
-                    cmx[ss][c] = key_dist(wb.key); cki[ss][c] = wb.idx; ccx[ss][c] = wb.x; ccy[ss][c] = wb.y; ccz[ss][c] = wb.z;
+                    cmx[ss][c] = key_dist(wb.key);
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
                         clo[ss][c][a] = rl[a]; chi[ss][c][a] = rh[a];
@@ -313,18 +326,63 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
         out_idx[0] = 0;
         if (out_xyz) { out_xyz[0] = ox; out_xyz[1] = oy; out_xyz[2] = oz; }
     }
-    __syncthreads();
 
-    long long pc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
+    // Work distribution.  Bucket (owner warp w, owner lane l, ss, c) is updated by warp (w + 4c + l) % NW: the dozen
+    // buckets around a new sample -- a few neighbouring super-buckets, i.e. neighbouring w, and their children c --
+    // land on different warps.  The queue is a bitmap (bit l of word (w, ss, c)); every lane of a consumer warp checks
+    // two of its words against a round-invariant pattern of the owner lanes that hash to this warp.
+    constexpr int WPL = kWords / 2;                  // bitmap words a consumer lane checks (32 lanes cover kBW * kWords words)
+    const int nwords = NW * kWords;
+    uint32_t pat[WPL];
+    {
+        uint32_t p0 = 0u;
+        for (int k = 0; k < 32; k += NW) p0 |= 1u << k;
+#pragma unroll
+        for (int h = 0; h < WPL; ++h) {
+            const int x = WPL * lane + h;
+            pat[h] = 0u;
+            if (x < nwords) {
+                const int wsrc = x / kWords, c = x % CH;
+                pat[h] = p0 << ((warp + 16 * NW - wsrc - 4 * c) % NW);
+            }
+        }
+    }
+    for (int i = tid; i < 2 * kBW * kWords; i += nthr) (&qmask[0][0])[i] = 0u;
+    const int kNone = __float_as_int(-1.f);
+    // largest (distance bits, then smallest rank of the buckets' candidate points) over the lanes; result in all lanes
+    auto better2 = [&](int ak, uint32_t ab, int bk, uint32_t bb) -> bool {
+        if (ak != bk) return ak > bk;
+        if (ak < 0) return false;
+        return rank_of(cidx[ab], lg_bs, cnt) < rank_of(cidx[bb], lg_bs, cnt);
+    };
+    auto warp_argmax = [&](int &k, uint32_t &bkt) {
+        const int kmax = __reduce_max_sync(kFullMask, k);
+        const unsigned eqm = __ballot_sync(kFullMask, k == kmax);
+        int srcl = __ffs(eqm) - 1;
+        if (kmax >= 0 && (eqm & (eqm - 1u))) {
+            const uint32_t r = k == kmax ? rank_of(cidx[bkt], lg_bs, cnt) : 0xffffffffu;
+            const uint32_t rm = __reduce_min_sync(kFullMask, r);
+            srcl = __ffs(__ballot_sync(kFullMask, r == rm)) - 1;
+        }
+        k = kmax;
+        bkt = __shfl_sync(kFullMask, bkt, srcl);
+    };
+    PN2_FPSB_BAR();
+
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0, nproc = 0;
     const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
     if (profiling) tprev = clock64();
-#define PN2_FPSB_MARK(i) if (profiling) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
+    // accumulated over the second half of the rounds only (steady state: a dozen buckets per round; the first rounds
+    // touch every bucket and would dominate an average)
+#define PN2_FPSB_MARK(i) if (profiling) { const long long tn = clock64(); if (j >= (m >> 1)) pc[i] += tn - tprev; tprev = tn; }
 
-    struct Buf { float4 p[PPL]; float d[PPL]; };
-
+    int cached_k = kNone;                            // this warp's best among its own buckets, valid while none of them is touched
+    uint32_t cached_b = 0u;
+    bool prev_touched = true;
+    struct Buf { float4 p[PPL]; float d[PPL]; float old; };
     for (int j = 1; j < m; ++j) {
         const int par = j & 1;
-        // ---- 1. which buckets can change? -------------------------------------------------------------------
+        // ---- 1. which buckets can change?  (owner threads; boxes and bucket maxima in registers) -------------
         uint32_t cm[SS];
 #pragma unroll
         for (int ss = 0; ss < SS; ++ss) {
@@ -336,110 +394,197 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
                         cm[ss] |= 1u << c;
             }
         }
-        PN2_FPSB_MARK(0)
-        // ---- 2. the owning warp updates them, two buckets in flight -----------------------------------------
-#pragma unroll
-        for (int ss = 0; ss < SS; ++ss) {
-            unsigned sm = __ballot_sync(kFullMask, cm[ss] != 0u);
-            if (sm == 0u) continue;
-            uint32_t cur = 0u;       // children still to do of lane `cl`
-            int cl = 0;
-            auto next = [&](int &l, int &c) -> bool {
-                if (cur == 0u) {
-                    if (sm == 0u) return false;
-                    cl = __ffs(sm) - 1; sm &= sm - 1u;
-                    cur = __shfl_sync(kFullMask, cm[ss], cl);
-                }
-                l = cl; c = __ffs(cur) - 1; cur &= cur - 1u;
-                return true;
-            };
-            auto load = [&](int l, int c, Buf &b) {
-                const uint32_t base = (uint32_t)((((ss * 32 + l) * kBW + warp) * CH + c) * BS);
-#pragma unroll
-                for (int q = 0; q < PPL; ++q) { b.p[q] = pts[base + q * 32 + lane]; b.d[q] = dist[base + q * 32 + lane]; }
-            };
-            auto process = [&](int l, int c, const Buf &b) {
-                const uint32_t base = (uint32_t)((((ss * 32 + l) * kBW + warp) * CH + c) * BS);
-                float nd[PPL];
-                bool ch = false;
-#pragma unroll
-                for (int q = 0; q < PPL; ++q) {
-                    nd[q] = fminf(sqdist3(b.p[q].x, b.p[q].y, b.p[q].z, ox, oy, oz), b.d[q]);   // sampling_gpu.cu:104-107
-                    ch |= nd[q] != b.d[q];
-                }
-                if (!__any_sync(kFullMask, ch)) return;
-                Cand best; best.key = 0u; best.idx = 0u; best.x = best.y = best.z = 0.f;
-#pragma unroll
-                for (int q = 0; q < PPL; ++q) {
-                    if (nd[q] != b.d[q]) dist[base + q * 32 + lane] = nd[q];
-                    const uint32_t key = dist_key(nd[q]), pi = (uint32_t)__float_as_int(b.p[q].w);
-                    if (cand_better(key, pi, best.key, best.idx, lg_bs, cnt)) { best.key = key; best.idx = pi; best.x = b.p[q].x; best.y = b.p[q].y; best.z = b.p[q].z; }
-                }
-                const Cand wb = warp_best(best, lg_bs, cnt);
-                if (lane == l) {
-#pragma unroll
-                    for (int cc = 0; cc < CH; ++cc)
-                        if (cc == c) { cmx[ss][cc] = key_dist(wb.key); cki[ss][cc] = wb.idx; ccx[ss][cc] = wb.x; ccy[ss][cc] = wb.y; ccz[ss][cc] = wb.z; }
-                }
-            };
-            Buf A, B;
-            int la, ca, lb, cb;
-            bool ha = next(la, ca), hb;
-            if (ha) load(la, ca, A);
-            while (ha) {
-                hb = next(lb, cb);
-                if (hb) load(lb, cb, B);
-                process(la, ca, A);
-                if (!hb) break;
-                ha = next(la, ca);
-                if (ha) load(la, ca, A);
-                process(lb, cb, B);
-            }
-            float s = cmx[ss][0];
-#pragma unroll
-            for (int c = 1; c < CH; ++c) s = fmaxf(s, cmx[ss][c]);
-            smax[ss] = s;
-        }
-        PN2_FPSB_MARK(1)
-        // ---- 3. argmax: thread -> warp -> table -> every warp -----------------------------------------------
-        Cand tb; tb.key = 0u; tb.idx = 0u; tb.x = tb.y = tb.z = 0.f;
+        // ---- 2. publish them: one ballot per (ss, c) ------------------------------------------------------------
+        uint32_t bal[kWords];
+        bool touched = false;
 #pragma unroll
         for (int ss = 0; ss < SS; ++ss)
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const uint32_t key = dist_key(cmx[ss][c]);
-                if (cand_better(key, cki[ss][c], tb.key, tb.idx, lg_bs, cnt)) { tb.key = key; tb.idx = cki[ss][c]; tb.x = ccx[ss][c]; tb.y = ccy[ss][c]; tb.z = ccz[ss][c]; }
+                bal[ss * CH + c] = __ballot_sync(kFullMask, (cm[ss] >> c) & 1u);
+                touched |= bal[ss * CH + c] != 0u;
             }
-        const Cand wb = warp_best(tb, lg_bs, cnt);
         if (lane == 0) {
-            table[par][warp] = make_uint4(wb.key, __float_as_uint(wb.x), __float_as_uint(wb.y), __float_as_uint(wb.z));
-            table_i[par][warp] = wb.idx;
+#pragma unroll
+            for (int ss = 0; ss < SS; ++ss)
+                *reinterpret_cast<uint4 *>(&qmask[par][warp * kWords + ss * CH]) =
+                    make_uint4(bal[ss * CH], bal[ss * CH + 1], bal[ss * CH + 2], bal[ss * CH + 3]);
         }
+        PN2_FPSB_MARK(0)
+        PN2_FPSB_BAR();
+        // ---- 3. every warp picks its share of the queue -------------------------------------------------------
+        uint32_t f[WPL];
+        bool anyf = false;
+        {
+            uint32_t q[WPL];
+            if (WPL == 2) {
+                const uint2 q2 = *reinterpret_cast<const uint2 *>(&qmask[par][2 * lane]);
+                q[0] = q2.x; q[1] = q2.y;
+            } else {
+#pragma unroll
+                for (int h4 = 0; h4 < WPL; h4 += 4) {
+                    const uint4 q4 = *reinterpret_cast<const uint4 *>(&qmask[par][WPL * lane + h4]);
+                    q[h4] = q4.x; q[h4 + 1] = q4.y; q[h4 + 2] = q4.z; q[h4 + 3] = q4.w;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < WPL; ++h) { f[h] = q[h] & pat[h]; anyf |= f[h] != 0u; }    // pat = 0 beyond the active warps' words
+        }
+        unsigned found = __ballot_sync(kFullMask, anyf);
+        if (profiling) { if (found == 0x12345678u) asm volatile("trap;"); nproc += __popc(found); }
+        PN2_FPSB_MARK(1)
+        int rk = kNone;                              // best of everything this warp accounts for in this round
+        uint32_t rb = 0u;
+        auto load = [&](uint32_t bkt, Buf &bf) {
+            const uint32_t base = bkt * BS;
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) { bf.p[q] = pts[base + q * 32 + lane]; bf.d[q] = dist[base + q * 32 + lane]; }
+            bf.old = meta4[bkt].x;
+        };
+        auto process = [&](uint32_t bkt, const Buf &bf) {
+            const uint32_t base = bkt * BS;
+            float nd[PPL];
+            bool ch = false;
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                nd[q] = fminf(sqdist3(bf.p[q].x, bf.p[q].y, bf.p[q].z, ox, oy, oz), bf.d[q]);   // sampling_gpu.cu:104-107
+                ch |= nd[q] != bf.d[q];
+            }
+            int key = __float_as_int(bf.old);
+            if (__any_sync(kFullMask, ch)) {
+                // lane's best point (PPL > 1), then the warp's: the lane that holds it writes the bucket's record
+                int bkey = __float_as_int(nd[0]);
+                uint32_t bi = (uint32_t)__float_as_int(bf.p[0].w);
+                float bx = bf.p[0].x, by = bf.p[0].y, bz = bf.p[0].z;
+                if (nd[0] != bf.d[0]) dist[base + lane] = nd[0];
+#pragma unroll
+                for (int q = 1; q < PPL; ++q) {
+                    if (nd[q] != bf.d[q]) dist[base + q * 32 + lane] = nd[q];
+                    const int k2 = __float_as_int(nd[q]);
+                    const uint32_t pi = (uint32_t)__float_as_int(bf.p[q].w);
+                    if (k2 > bkey || (k2 == bkey && k2 >= 0 && rank_of(pi, lg_bs, cnt) < rank_of(bi, lg_bs, cnt))) {
+                        bkey = k2; bi = pi; bx = bf.p[q].x; by = bf.p[q].y; bz = bf.p[q].z;
+                    }
+                }
+                key = __reduce_max_sync(kFullMask, bkey);
+                const unsigned eqm = __ballot_sync(kFullMask, bkey == key);
+                int srcl = __ffs(eqm) - 1;
+                if (key >= 0 && (eqm & (eqm - 1u))) {    // several lanes hold the maximum: smallest rank wins
+                    const uint32_t r = bkey == key ? rank_of(bi, lg_bs, cnt) : 0xffffffffu;
+                    const uint32_t rm = __reduce_min_sync(kFullMask, r);
+                    srcl = __ffs(__ballot_sync(kFullMask, r == rm)) - 1;
+                }
+                if (lane == srcl) { meta4[bkt] = make_float4(__int_as_float(key), bx, by, bz); cidx[bkt] = bi; }
+            }
+            if (key == rk && key >= 0) __syncwarp();     // the tie-break reads cidx[bkt], possibly just written
+            if (better2(key, bkt, rk, rb)) { rk = key; rb = bkt; }
+        };
+        // entries: for each lane L in `found`, the set bits of its two words; word x = 2L + h -> (owner warp, ss, c)
+        uint32_t g[WPL], gl = 0u;
+#pragma unroll
+        for (int h = 0; h < WPL; ++h) g[h] = 0u;
+        auto next = [&](uint32_t &bkt) -> bool {
+            bool left = false;
+#pragma unroll
+            for (int h = 0; h < WPL; ++h) left |= g[h] != 0u;
+            if (!left) {
+                if (found == 0u) return false;
+                gl = (uint32_t)__ffs(found) - 1u; found &= found - 1u;
+#pragma unroll
+                for (int h = 0; h < WPL; ++h) g[h] = __shfl_sync(kFullMask, f[h], (int)gl);
+            }
+            uint32_t hh = 0u, bits = 0u;
+#pragma unroll
+            for (int h = WPL - 1; h >= 0; --h)
+                if (g[h]) { hh = (uint32_t)h; bits = g[h]; }
+            const uint32_t ol = (uint32_t)__ffs(bits) - 1u;              // owner lane
+#pragma unroll
+            for (int h = 0; h < WPL; ++h)
+                if ((uint32_t)h == hh) g[h] &= g[h] - 1u;
+            const uint32_t x = WPL * gl + hh, wsrc = x / kWords, sc = x % kWords;
+            bkt = (((sc / CH) * 32u + ol) * (uint32_t)NW + wsrc) * CH + (sc % CH);
+            return true;
+        };
+        Buf A, B;
+        uint32_t ba = 0, bb = 0;
+        bool ha = next(ba), hb = false;
+        if (ha) load(ba, A);
+        // while the first loads are in flight: the best of this warp's OWN buckets that are not in the queue (their
+        // maxima and candidates do not change this round); cached while none of the warp's buckets is touched
+        if (touched || prev_touched) {
+            int tk = kNone;
+            uint32_t tb = 0u;
+#pragma unroll
+            for (int ss = 0; ss < SS; ++ss)
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int key = ((cm[ss] >> c) & 1u) ? kNone : __float_as_int(cmx[ss][c]);
+                    const uint32_t bkt = (uint32_t)((((ss * 32 + lane) * NW + warp) * CH) + c);
+                    if (better2(key, bkt, tk, tb)) { tk = key; tb = bkt; }
+                }
+            warp_argmax(tk, tb);
+            if (!touched) { cached_k = tk; cached_b = tb; }
+            rk = tk; rb = tb;
+        } else {
+            rk = cached_k; rb = cached_b;
+        }
+        prev_touched = touched;
+        while (ha) {
+            hb = next(bb);
+            if (hb) load(bb, B);
+            process(ba, A);
+            if (!hb) break;
+            ha = next(ba);
+            if (ha) load(ba, A);
+            process(bb, B);
+        }
+        if (lane == 0) tableA[warp] = make_int2(rk, (int)rb);
         PN2_FPSB_MARK(2)
-        __syncthreads();
+        PN2_FPSB_BAR();
+        // ---- 4. argmax over the warps' entries (every warp, redundantly) ----------------------------------------
+        int bk = kNone;
+        uint32_t bbk = 0u;
+        if (lane < NW) { const int2 t = tableA[lane]; bk = t.x; bbk = (uint32_t)t.y; }
+        if (profiling) { if (bk == 0x7ffffff0) asm volatile("trap;"); }
         PN2_FPSB_MARK(3)
-        Cand e; e.key = 0u; e.idx = 0u; e.x = e.y = e.z = 0.f;
-        if (lane < kBW) {
-            const uint4 t = table[par][lane];
-            e.key = t.x; e.x = __uint_as_float(t.y); e.y = __uint_as_float(t.z); e.z = __uint_as_float(t.w);
-            e.idx = table_i[par][lane];
+        warp_argmax(bk, bbk);
+        const bool none = bk < 0;         // every point skipped: the reference's reduction leaves besti = 0
+        uint32_t widx = 0u;
+        ox = p0x; oy = p0y; oz = p0z;
+        if (!none) {
+            const float4 w4 = meta4[bbk];
+            ox = w4.y; oy = w4.z; oz = w4.w;
+            widx = cidx[bbk];
         }
-        const Cand win = warp_best(e, lg_bs, cnt);
-        const bool none = win.key == 0u;   // every point skipped: the reference's reduction leaves besti = 0
-        ox = none ? p0x : win.x; oy = none ? p0y : win.y; oz = none ? p0z : win.z;
-        if (tid == (j & (kBT - 1))) {
-            out_idx[j] = none ? 0 : (int)win.idx;
+        if (tid == (j & 127)) {
+            out_idx[j] = (int)widx;
             if (out_xyz) { out_xyz[3 * (size_t)j] = ox; out_xyz[3 * (size_t)j + 1] = oy; out_xyz[3 * (size_t)j + 2] = oz; }
+        }
+        // the owners pick up the new maxima of their updated buckets
+#pragma unroll
+        for (int ss = 0; ss < SS; ++ss) {
+            if (cm[ss]) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    if ((cm[ss] >> c) & 1u) cmx[ss][c] = meta4[(((ss * 32 + lane) * NW + warp) * CH) + c].x;
+                float sx = cmx[ss][0];
+#pragma unroll
+                for (int c = 1; c < CH; ++c) sx = fmaxf(sx, cmx[ss][c]);
+                smax[ss] = sx;
+            }
         }
         PN2_FPSB_MARK(4)
     }
-    if (profiling)
+    if (profiling) {
         for (int i = 0; i < 6; ++i) prof[i] = pc[i];
+        prof[6] = nproc;
+    }
 #undef PN2_FPSB_MARK
+#undef PN2_FPSB_BAR
 }
 
 struct BucketCfg {
-    int ppl, ss;
+    int ppl, ss, nwa;
     bool sdist;
     int npad;
     size_t smem, stride;
@@ -459,9 +604,16 @@ bool choose(int n, BucketCfg *c)
     const int bs = 32 * ppl;
     c->ppl = ppl; c->ss = ss;
     c->npad = (n + bs - 1) / bs * bs;
-    c->sdist = (size_t)c->npad * 4 <= kMaxSmem;
-    const size_t h = (size_t)kCells * 4;
-    c->smem = c->sdist && (size_t)c->npad * 4 > h ? (size_t)c->npad * 4 : h;
+    const size_t meta = (size_t)20 * (c->npad / bs);              // per bucket: float4 record + candidate index
+    // warps that run the rounds: one thread per super-bucket of CH buckets, at least four warps
+    const int nsup = (c->npad / bs + kCH - 1) / kCH;
+    c->nwa = (nsup + 32 * ss - 1) / (32 * ss);
+    if (c->nwa < 4) c->nwa = 4;
+    if (c->nwa > kBW) return false;
+    c->sdist = (size_t)c->npad * 4 + meta <= kMaxSmem;
+    const size_t h = (size_t)kCells * 4, need = (c->sdist ? (size_t)c->npad * 4 : 0) + meta;
+    if (need > kMaxSmem) return false;
+    c->smem = need > h ? need : h;
     const size_t bytes = (size_t)20 * c->npad + (size_t)2 * n;
     c->stride = (bytes + 255) / 256 * 256;
     return true;
@@ -474,7 +626,7 @@ int launch_cfg(const BucketCfg &c, int b, int n, int m, int lg_bs, int cnt, cons
     auto kern = fps_bucket_kernel<PPL, kCH, SS, SDIST>;
     PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     kern<<<b, kBT, c.smem, stream>>>(n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy,
-                                     static_cast<unsigned char *>(ws), c.stride, c.npad, prof);
+                                     static_cast<unsigned char *>(ws), c.stride, c.npad, c.nwa, prof);
     PN2_LAUNCH_CHECK("fps_bucket_kernel");
     return PN2_OK;
 }

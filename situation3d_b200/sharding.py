@@ -57,6 +57,51 @@ class FlatGradAllReduce:
     def zero(self):
         self.flat.zero_()
 
+    # ---- overlap with backward ---------------------------------------------------------------------------
+    def enable_overlap(self, nchunks=3, stream=None):
+        """Split the bucket into ``nchunks`` contiguous chunks (whole parameters, in ``module.parameters()`` order =
+        forward order) and all-reduce each chunk on ``stream`` as soon as backward has produced its last gradient --
+        the chunk's FIRST parameter, since backward visits the layers in reverse.  ``finish()`` then waits for the
+        collectives and divides by the world size.  With one rank nothing is hooked."""
+        self.chunks, self._handles, self._pending = [], [], []
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return self
+        self.comm_stream = stream
+        total, target, start, off = self.flat.numel(), self.flat.numel() / float(nchunks), 0, 0
+        firsts = []
+        first = 0
+        for i, p in enumerate(self.params):
+            off += p.numel()
+            if off - start >= target or i == len(self.params) - 1:
+                self.chunks.append((start, off))
+                firsts.append(first)
+                start, first = off, i + 1
+        for (lo, hi), fi in zip(self.chunks, firsts):
+            self._handles.append(self.params[fi].register_post_accumulate_grad_hook(self._make_hook(lo, hi)))
+        return self
+
+    def _make_hook(self, lo, hi):
+        def hook(_param):
+            chunk = self.flat[lo:hi]
+            if self.comm_stream is not None:
+                self.comm_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.comm_stream):
+                    self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return hook
+
+    def finish(self):
+        """After backward: wait for the chunk collectives launched by the hooks and average."""
+        if not getattr(self, "chunks", None):
+            return
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.flat.div_(dist.get_world_size(self.group))
+
     def allreduce(self, async_op=False):
         """SUM over ranks then divide by the world size (gradient averaging)."""
         world = dist.get_world_size(self.group)

@@ -49,6 +49,16 @@ def _worker(rank, world, port, ret):
         torch.testing.assert_close(bucket.flat, sum(gathered) / world)
         for p, v in zip(net.parameters(), bucket.views):
             assert p.grad.data_ptr() == v.data_ptr()                     # grads live in the bucket
+        # chunked all-reduce started by hooks during backward gives the same averaged gradients
+        net2 = torch.nn.Sequential(torch.nn.Conv2d(4, 6, 1, bias=False), torch.nn.BatchNorm2d(6), torch.nn.ReLU(),
+                                   torch.nn.Conv2d(6, 3, 1))
+        net2.load_state_dict(net.state_dict())
+        b2 = FlatGradAllReduce(net2).enable_overlap(nchunks=2)
+        assert len(b2.chunks) == 2 and b2.chunks[0][0] == 0 and b2.chunks[-1][1] == b2.flat.numel()
+        b2.zero()
+        net2(x).square().mean().backward()
+        b2.finish()
+        torch.testing.assert_close(b2.flat, bucket.flat)
         # BatchNorm statistics are NOT synchronised (the reference has no SyncBN): they differ across ranks
         stats = [torch.zeros(6) for _ in range(world)]
         dist.all_gather(stats, net[1].running_mean.clone())

@@ -489,6 +489,38 @@ def test_backbone_pipeline_from_host_buffers():
         pipe.drain()
 
 
+def test_row_layout_training_matches_reference_wiring():
+    """Training mode on channel-last rows (train_rows.py) against the operator-by-operator wiring of the reference
+    (QueryAndGroup -> NCHW SharedMLP -> max_pool2d, autograd through the *_grad kernels): same loss, same gradients
+    for every parameter, same BatchNorm running statistics, same indices."""
+    import copy
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.synthetic import make_batch
+    torch.manual_seed(0)
+    a = Pointnet2Backbone(input_feature_dim=9, npoints=(256, 128, 64, 32)).cuda().train()
+    b = copy.deepcopy(a)
+    b.train_layout = "reference"
+    pc = torch.from_numpy(make_batch(2, 3000, 9)).cuda()
+    oa, ob = a({"point_clouds": pc}), b({"point_clouds": pc})
+    for k in ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds"):
+        assert torch.equal(oa[k], ob[k]), k
+    torch.testing.assert_close(oa["fp2_features"], ob["fp2_features"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(oa["sa2_features"], ob["sa2_features"], rtol=1e-3, atol=1e-4)
+    la, lb = oa["fp2_features"].square().mean(), ob["fp2_features"].square().mean()
+    la.backward()
+    lb.backward()
+    torch.testing.assert_close(la, lb, rtol=1e-4, atol=1e-6)
+    for (n1, p1), (_, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert p1.grad is not None, n1
+        scale = float(p2.grad.abs().max()) + 1e-12
+        assert float((p1.grad - p2.grad).abs().max()) <= 5e-3 * scale, n1
+    for (n1, t1), (_, t2) in zip(a.named_buffers(), b.named_buffers()):
+        if t1.dtype.is_floating_point:
+            torch.testing.assert_close(t1, t2, rtol=1e-3, atol=1e-5, msg=n1)
+        else:
+            assert torch.equal(t1, t2), n1
+
+
 def test_compact_input_is_bit_identical():
     """fp32 coordinates + bf16 feature rows (Pointnet2Backbone.pack_point_clouds: half the host-to-device bytes) give
     bit-identical results to the reference's fp32 point_clouds on the bf16 arm, eagerly and through the pipeline from
