@@ -636,8 +636,13 @@ int launch_cfg(const BucketCfg &c, int b, int n, int m, int lg_bs, int cnt, cons
 // smallest scene the bucketed kernel is used for (below, the register-resident kernels of fps.cu win)
 int fps_bucket_min_points()
 {
+    // Measured on B200 (scripts/fps_bucket_bench.py, B = 8): at 40 000 points the register-resident cluster kernel is
+    // the faster launch (1.36 ms against 4.1 ms: a round here is a chain of ~430 dependent warp instructions); at
+    // 200 000 points this kernel is (12.3 ms against 15.6 ms) and needs one SM per scene instead of sixteen half-SMs
+    // (1.76 ms against 9.0 ms per 8-scene batch with several batches in flight).  Default: beyond what the cluster
+    // kernel covers with 8 CTAs.
     const char *e = getenv("PN2_FPS_BUCKET_MIN");    // tests / sweeps: 1 = always, a huge value = never
-    return e ? atoi(e) : 8193;
+    return e ? atoi(e) : 81921;
 }
 
 size_t fps_bucket_workspace_bytes(int b, int n)

@@ -124,6 +124,124 @@ reencode_kernel(int t, int d, int h, int mode, const float *__restrict__ tokens,
     }
 }
 
+// ---- v2: persistent CTAs, W2 resident in shared memory, 8 tokens x 8 outputs per thread on packed FFMA -------------
+// The kernel above re-stages W2 (d x h fp32 = 128 KB for the reference's 256 x 128) for every 32 tokens and spends one
+// shared-memory read per two FMAs.  Here a CTA loads W2 transposed ONCE (W2T[h][d]: a lane's outputs are two float4
+// groups, conflict-free) and walks 64-token tiles: positions -> hidden activations (exact-erf GELU) -> the d x h
+// product with each thread holding 8 tokens x 8 outputs in registers as fp32x2 pairs: per hidden unit 4 LDS.128 feed
+// 32 fma.rn.f32x2 (64 FMAs).  tokens are read once, the sum is written once.  Used when W2T + the tile fit in 200 KB.
+constexpr int kTok2 = 64;
+
+__device__ __forceinline__ unsigned long long re_pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long re_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kReThreads, 1)
+reencode_v2_kernel(int b, int t, int h, int mode, const float *__restrict__ tokens, const float *__restrict__ positions,
+                   const float *__restrict__ situation, const float *__restrict__ w1, const float *__restrict__ b1,
+                   const float *__restrict__ w2, const float *__restrict__ b2, float *__restrict__ out,
+                   float *__restrict__ new_pos, int tiles_per_scene)
+{
+    static_assert(D == 256, "a lane owns outputs 4*lane..+3 and 128 + 4*lane..+3");
+    extern __shared__ __align__(16) float re2_smem[];
+    float *w2t = re2_smem;                       // [h][D]
+    float *hid = w2t + (size_t)h * D;            // [h][kTok2]
+    float *pxy = hid + (size_t)h * kTok2;        // [kTok2][2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // W2 (D, h) row-major -> W2T[h][D]: lanes take consecutive outputs (conflict-free stores; the strided global reads
+    // come out of L2 once per CTA)
+    for (int i = tid; i < h * D; i += kReThreads) {
+        const int dd = i % D, hh = i / D;
+        w2t[hh * D + dd] = __ldg(w2 + (size_t)dd * h + hh);
+    }
+    const float4 bias_lo = __ldg(reinterpret_cast<const float4 *>(b2) + lane);
+    const float4 bias_hi = __ldg(reinterpret_cast<const float4 *>(b2 + 128) + lane);
+    const int ntiles = b * tiles_per_scene;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int bi = tile / tiles_per_scene, tok0 = (tile - bi * tiles_per_scene) * kTok2;
+        const int ntok = min(kTok2, t - tok0);
+        __syncthreads();                         // W2T staged / previous tile's hid consumed
+        if (tid < kTok2) {
+            float q[3] = {0.f, 0.f, 0.f};
+            if (tid < ntok) {
+                const float *pp = positions + ((size_t)bi * t + tok0 + tid) * 3;
+                float R[9], tr[3];
+                quat_matrix(situation + (size_t)bi * 7, R, tr);
+                const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+                if (mode == 0) {          // p' = R p + t            (temp.py:90-97)
+                    q[0] = fmaf(pz, R[2], fmaf(py, R[1], px * R[0])) + tr[0];
+                    q[1] = fmaf(pz, R[5], fmaf(py, R[4], px * R[3])) + tr[1];
+                    q[2] = fmaf(pz, R[8], fmaf(py, R[7], px * R[6])) + tr[2];
+                } else {                  // agent frame: p' = R^T (p - t)
+                    const float ux = px - tr[0], uy = py - tr[1], uz = pz - tr[2];
+                    q[0] = fmaf(uz, R[6], fmaf(uy, R[3], ux * R[0]));
+                    q[1] = fmaf(uz, R[7], fmaf(uy, R[4], ux * R[1]));
+                    q[2] = fmaf(uz, R[8], fmaf(uy, R[5], ux * R[2]));
+                }
+                if (new_pos) {
+                    float *np = new_pos + ((size_t)bi * t + tok0 + tid) * 3;
+                    np[0] = q[0]; np[1] = q[1]; np[2] = q[2];
+                }
+            }
+            pxy[2 * tid] = q[0]; pxy[2 * tid + 1] = q[1];
+        }
+        __syncthreads();
+        // hidden layer: Linear(2, h) + exact GELU (sqa_module.py:274-276), stored [h][token]
+        for (int e = tid; e < h * kTok2; e += kReThreads) {
+            const int i = e % kTok2, jj = e / kTok2;
+            hid[e] = gelu_erf(fmaf(pxy[2 * i + 1], __ldg(w1 + 2 * jj + 1), fmaf(pxy[2 * i], __ldg(w1 + 2 * jj), __ldg(b1 + jj))));
+        }
+        __syncthreads();
+        // product: warp -> tokens 8*warp .. 8*warp+7, lane -> outputs 4*lane..+3 and 128 + 4*lane..+3
+        unsigned long long acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i][0] = re_pack2(bias_lo.x, bias_lo.y); acc[i][1] = re_pack2(bias_lo.z, bias_lo.w);
+            acc[i][2] = re_pack2(bias_hi.x, bias_hi.y); acc[i][3] = re_pack2(bias_hi.z, bias_hi.w);
+        }
+#pragma unroll 2
+        for (int jj = 0; jj < h; ++jj) {
+            const float4 wl = *reinterpret_cast<const float4 *>(w2t + (size_t)jj * D + 4 * lane);
+            const float4 wh = *reinterpret_cast<const float4 *>(w2t + (size_t)jj * D + 128 + 4 * lane);
+            const float4 ha = *reinterpret_cast<const float4 *>(hid + (size_t)jj * kTok2 + 8 * warp);
+            const float4 hb = *reinterpret_cast<const float4 *>(hid + (size_t)jj * kTok2 + 8 * warp + 4);
+            const unsigned long long w0 = re_pack2(wl.x, wl.y), w1p = re_pack2(wl.z, wl.w), w2p = re_pack2(wh.x, wh.y),
+                                     w3 = re_pack2(wh.z, wh.w);
+            const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned long long hh2 = re_pack2(hv[i], hv[i]);
+                acc[i][0] = re_fma2(hh2, w0, acc[i][0]); acc[i][1] = re_fma2(hh2, w1p, acc[i][1]);
+                acc[i][2] = re_fma2(hh2, w2p, acc[i][2]); acc[i][3] = re_fma2(hh2, w3, acc[i][3]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int tk = 8 * warp + i;
+            if (tk < ntok) {
+                const size_t o = ((size_t)bi * t + tok0 + tk) * D;
+                const float4 tl = __ldg(reinterpret_cast<const float4 *>(tokens + o) + lane);
+                const float4 th = __ldg(reinterpret_cast<const float4 *>(tokens + o + 128) + lane);
+                float a[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) asm("mov.b64 {%0, %1}, %2;" : "=f"(a[2 * q]), "=f"(a[2 * q + 1]) : "l"(acc[i][q]));
+                reinterpret_cast<float4 *>(out + o)[lane] = make_float4(tl.x + a[0], tl.y + a[1], tl.z + a[2], tl.w + a[3]);
+                reinterpret_cast<float4 *>(out + o + 128)[lane] = make_float4(th.x + a[4], th.y + a[5], th.z + a[6], th.w + a[7]);
+            }
+        }
+    }
+}
+
 // prior[b, i] = w_i / sum_i w_i,  w_i = exp(-|p_xy - t_xy|^2 / (2 sigma^2))   (sqa_module.py:332-336)
 __global__ void __launch_bounds__(256)
 prior_kernel(int t, float sigma, const float *__restrict__ positions, const float *__restrict__ situation,
@@ -202,14 +320,27 @@ extern "C" int pn2_reencode_forward(int b, int t, int d, int h, int mode, float 
     if (b < 0 || t < 0 || d < 1 || h < 1 || (mode != 0 && mode != 1)) return PN2_ERR_INVALID_ARGUMENT;
     if (b == 0 || t == 0) return PN2_OK;
     if (!tokens || !positions || !situation || !w1 || !b1 || !w2 || !b2 || !out) return PN2_ERR_INVALID_ARGUMENT;
-    const int hp = (h + 3) / 4 * 4;
-    const size_t smem = sizeof(float) * ((size_t)kTok * hp + (size_t)kSlab * (kReThreads + 1) + 2 * kTok);
-    if (smem > 200 * 1024) return PN2_ERR_INVALID_ARGUMENT;
-    PN2_CUDA_TRY(cudaFuncSetAttribute(reencode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    const int groups = ceil_div(t, kTok);
-    reencode_kernel<<<(unsigned)((long long)b * groups), kReThreads, smem, as_stream(stream)>>>(
-        t, d, h, mode, tokens, positions, situation, w1, b1, w2, b2, out, new_pos, groups);
-    PN2_LAUNCH_CHECK("reencode");
+    const size_t smem2 = sizeof(float) * ((size_t)h * 256 + (size_t)h * kTok2 + 2 * kTok2);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(tokens) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(b2)) & 15) == 0;
+    if (d == 256 && smem2 <= 200 * 1024 && aligned) {
+        // the reference's shape (Linear(128, 256)): W2 resident per CTA, persistent over 64-token tiles
+        PN2_CUDA_TRY(cudaFuncSetAttribute(reencode_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const int tiles_per_scene = ceil_div(t, kTok2);
+        const long long ntiles = (long long)b * tiles_per_scene;
+        const int grid = (int)(ntiles < stream_sm_count(as_stream(stream)) ? ntiles : stream_sm_count(as_stream(stream)));
+        reencode_v2_kernel<256><<<grid, kReThreads, smem2, as_stream(stream)>>>(b, t, h, mode, tokens, positions, situation,
+                                                                              w1, b1, w2, b2, out, new_pos, tiles_per_scene);
+        PN2_LAUNCH_CHECK("reencode_v2");
+    } else {
+        const int hp = (h + 3) / 4 * 4;
+        const size_t smem = sizeof(float) * ((size_t)kTok * hp + (size_t)kSlab * (kReThreads + 1) + 2 * kTok);
+        if (smem > 200 * 1024) return PN2_ERR_INVALID_ARGUMENT;
+        PN2_CUDA_TRY(cudaFuncSetAttribute(reencode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const int groups = ceil_div(t, kTok);
+        reencode_kernel<<<(unsigned)((long long)b * groups), kReThreads, smem, as_stream(stream)>>>(
+            t, d, h, mode, tokens, positions, situation, w1, b1, w2, b2, out, new_pos, groups);
+        PN2_LAUNCH_CHECK("reencode");
+    }
     if (prior) {
         if (!(sigma > 0.f)) return PN2_ERR_INVALID_ARGUMENT;
         prior_kernel<<<b, 256, 0, as_stream(stream)>>>(t, sigma, positions, situation, prior);

@@ -40,8 +40,11 @@ def test_library_basics_without_gpu():
     assert _lib.lib.pn2_mlp_f32_supported(3, dims) == 1
     assert _lib.lib.pn2_mlp_f32_supported(2, _lib.int_array([4096, 4096, 64])) == 0
     # large scenes: the bucketed kernel's scratch, per scene 20 bytes per (padded) point + 2 per point, 256-byte aligned
-    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 40000, 2048) == 8 * ((20 * 40000 + 2 * 40000 + 255) // 256 * 256)
-    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 2048, 1024) == 0    # small scenes: register-resident
+    # large scenes: the bucketed kernel's scratch, per scene 20 bytes per point (padded to whole 128-point buckets) + 2
+    # per point, 256-byte aligned
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 200000, 4096) == 8 * ((20 * 200064 + 2 * 200000 + 255) // 256 * 256)
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 40000, 2048) == 0   # register-resident cluster kernel
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 2048, 1024) == 0
     # argument validation happens before any CUDA call
     assert _lib.lib.pn2_gather_points(-1, 1, 1, 1, None, None, None, None) == -1
     assert _lib.lib.pn2_ball_query(1, 10, 4, 0.5, 8, None, None, None, None) == -1
