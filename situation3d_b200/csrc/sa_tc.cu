@@ -647,36 +647,46 @@ sa_tc_v3_kernel(const SaTcParams p)
         // Global-load latencies are taken off the per-tile critical path: the neighbour index of this lane's row
         // is fetched two tiles ahead, the row's and the centre's coordinates (addressed by that index) one tile
         // ahead.
+        // No integer division anywhere in the per-tile path: a gather warp's iteration is a chain of dependent
+        // instructions (the 4 warps work on the SAME tile), so its length IS the kernel's tile rate.  Rows and
+        // centres are addressed by their global (batch-spanning) numbers -- tiles_per_scene * 128 = npoint * NS --
+        // and the scene index of a tile advances incrementally with the tile stride.
         auto load_idx = [&](int it_) -> int {
             if (it_ >= nt) return 0;
-            const int t_ = blockIdx.x + it_ * gridDim.x, b_ = t_ / p.tiles_per_scene;
-            return __ldg(p.idx + (size_t)b_ * p.npoint * NS + (t_ - b_ * p.tiles_per_scene) * kTile + myrow);
+            const int t_ = blockIdx.x + it_ * gridDim.x;
+            return __ldg(p.idx + (size_t)t_ * kTile + myrow);
         };
         // coordinates in flight for tiles it+1 and it+2 (slot = tile parity), indices for it+2 and it+3
         float px[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, cx[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-        auto load_xyz = [&](int it_, int nb_, float (&pv)[3], float (&cv)[3]) {
+        auto load_xyz = [&](int it_, int b_, int nb_, float (&pv)[3], float (&cv)[3]) {
             if (it_ >= nt) return;
-            const int t_ = blockIdx.x + it_ * gridDim.x, b_ = t_ / p.tiles_per_scene;
-            const int r0_ = (t_ - b_ * p.tiles_per_scene) * kTile;
+            const int t_ = blockIdx.x + it_ * gridDim.x;
             const float *pp = p.xyz + ((size_t)b_ * p.n + nb_) * 3;
-            const float *cc = p.new_xyz + ((size_t)b_ * p.npoint + (r0_ + myrow) / NS) * 3;
+            const float *cc = p.new_xyz + (size_t)((t_ * kTile + myrow) / NS) * 3;
 #pragma unroll
             for (int a = 0; a < 3; ++a) { pv[a] = __ldg(pp + a); cv[a] = __ldg(cc + a); }
         };
+        // scene index of tiles it, it+1, it+2 (bq[0..2]) and the position of tile it+2 inside its scene
+        int bq[3], rem2;
+        {
+            const int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x, t2 = blockIdx.x + 2 * gridDim.x;
+            bq[0] = t0 / p.tiles_per_scene; bq[1] = t1 / p.tiles_per_scene; bq[2] = t2 / p.tiles_per_scene;
+            rem2 = t2 - bq[2] * p.tiles_per_scene;
+        }
+        int rg = 0, rg_phase = 1;          // region of tile itt and the parity to wait for on its `empty` barrier
+        int pg = 0;                        // region of the tile being published (itt - lag)
         const bool fixed_rows = (p.debug & 32) != 0;
         int nb0 = fixed_rows ? myrow : load_idx(0), nb1 = fixed_rows ? myrow : load_idx(1);   // tiles it, it+1
         int nb2 = fixed_rows ? myrow : load_idx(2);                                           // tile it+2
-        load_xyz(0, nb0, px[0], cx[0]);
-        load_xyz(1, nb1, px[1], cx[1]);
+        load_xyz(0, bq[0], nb0, px[0], cx[0]);
+        load_xyz(1, bq[1], nb1, px[1], cx[1]);
         for (int it = 0; it < nt; it += 2) {
 #pragma unroll
           for (int par = 0; par < 2; ++par) {
             const int itt = it + par;
             if (itt >= nt) break;
-            const int tile = blockIdx.x + itt * gridDim.x;
-            const int rg = itt % R, u = itt / R;
             const int nb = nb0;
-            const int bi = tile / p.tiles_per_scene;
+            const int bi = bq[0];
             // recentred, normalised xyz of this lane's row, from the coordinates loaded two tiles ago
             float h[3], l[3];
 #pragma unroll
@@ -686,9 +696,12 @@ sa_tc_v3_kernel(const SaTcParams p)
                 l[a] = d - h[a];
             }
             nb0 = nb1; nb1 = nb2;
-            load_xyz(itt + 2, nb1, px[par], cx[par]);
+            load_xyz(itt + 2, bq[2], nb1, px[par], cx[par]);
             nb2 = fixed_rows ? myrow : load_idx(itt + 3);
-            if (u > 0) tc_mbar_wait(bar_empty + 8u * rg, (u - 1) & 1);
+            bq[0] = bq[1]; bq[1] = bq[2];
+            rem2 += (int)gridDim.x;
+            while (rem2 >= p.tiles_per_scene) { rem2 -= p.tiles_per_scene; ++bq[2]; }
+            if (itt >= R) tc_mbar_wait(bar_empty + 8u * rg, (uint32_t)rg_phase);
             PN2_MARK(0)
             unsigned char *region = ring + (size_t)rg * s.region_bytes;
             const uint32_t a_base = smem_u32(region);
@@ -714,8 +727,10 @@ sa_tc_v3_kernel(const SaTcParams p)
                 else asm volatile("cp.async.wait_group 0;" ::: "memory");
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) tc_mbar_arrive(bar_full + 8u * ((itt - lag) % R));
+                if (lane == 0) tc_mbar_arrive(bar_full + 8u * pg);
+                pg = pg + 1 == R ? 0 : pg + 1;
             }
+            if (++rg == R) { rg = 0; rg_phase ^= 1; }
             PN2_MARK(2)
           }
         }
@@ -724,7 +739,7 @@ sa_tc_v3_kernel(const SaTcParams p)
         fence_proxy_async();
         __syncwarp();
         if (lane == 0)
-            for (int it = max(nt - lag, 0); it < nt; ++it) tc_mbar_arrive(bar_full + 8u * (it % R));
+            for (int it = max(nt - lag, 0); it < nt; ++it) { tc_mbar_arrive(bar_full + 8u * pg); pg = pg + 1 == R ? 0 : pg + 1; }
         if (PROF) { if (profiling) for (int i = 0; i < 3; ++i) p.prof[16 + i] = pc[i]; }
     } else if (warp == kV3WarpA) {
         // ===== layer-1 issuer =====
@@ -733,9 +748,10 @@ sa_tc_v3_kernel(const SaTcParams p)
         const uint32_t elected = elect_one();
         const bool profiling = prof_cta && lane == 0;
         if (PROF) { if (profiling) tprev = clock64(); }
+        int rg = 0, rg_phase = 0;                                              // it % R and (it / R) & 1, kept incrementally
         for (int it = 0; it < nt; ++it) {
-            const int sl = it % T, w = it / T, rg = it % R;
-            tc_mbar_wait(bar_full + 8u * rg, (it / R) & 1);                    // gathered
+            const int sl = it % T, w = it / T;
+            tc_mbar_wait(bar_full + 8u * rg, (uint32_t)rg_phase);               // gathered
             PN2_MARK(0)
             if (w > 0) tc_mbar_wait(bar_tfree + 8u * sl, (w - 1) & 1);         // the slot's previous tile has left TMEM
             PN2_MARK(1)
@@ -745,6 +761,7 @@ sa_tc_v3_kernel(const SaTcParams p)
                        idesc1, elected);
             if (elected) umma_commit(bar_dfull + 8u * (sl * 3 + 0));
             __syncwarp();
+            if (++rg == R) { rg = 0; rg_phase ^= 1; }
             PN2_MARK(2)
         }
         if (PROF) { if (profiling) for (int i = 0; i < 3; ++i) p.prof[8 + i] = pc[i]; }
@@ -778,8 +795,9 @@ sa_tc_v3_kernel(const SaTcParams p)
         const uint32_t elected = elect_one();
         const bool profiling = prof_cta && lane == 0;
         if (PROF) { if (profiling) tprev = clock64(); }
+        int rg = 0;                                                            // it % R, kept incrementally
         for (int it = 0; it < nt; ++it) {
-            const int sl = it % T, w = it / T, rg = it % R;
+            const int sl = it % T, w = it / T;
             tc_mbar_wait(bar_aready + 8u * (sl * 2 + 1), w & 1);               // A2 in the region, D2 drained
             PN2_MARK(0)
             tc_fence_after();
@@ -791,6 +809,7 @@ sa_tc_v3_kernel(const SaTcParams p)
                 umma_commit(bar_dfull + 8u * (sl * 3 + 2));
                 umma_commit(bar_empty + 8u * rg);                               // region free for the gather warps
             }
+            if (++rg == R) rg = 0;
             __syncwarp();
             PN2_MARK(1)
         }
@@ -806,6 +825,10 @@ sa_tc_v3_kernel(const SaTcParams p)
         const bool profiling = prof_cta && tid == 0;
         if (PROF) { if (profiling) tprev = clock64(); }
         const int nk = nt > grp ? (nt - grp + 1) / 2 : 0;
+        // the group's tiles are grp, grp + 2, ...: region and scene index advance incrementally (no division per tile)
+        int rg2 = grp % R;
+        int bi3 = (int)((blockIdx.x + grp * gridDim.x) / p.tiles_per_scene);
+        int rem3 = (int)(blockIdx.x + grp * gridDim.x) - bi3 * p.tiles_per_scene;
         auto epi1 = [&](int it) {
             const int sl = it % T;
             tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 0), (uint32_t)((it / T) & 1));
@@ -819,7 +842,9 @@ sa_tc_v3_kernel(const SaTcParams p)
         };
         auto epi2 = [&](int it) {
             const int sl = it % T;
-            unsigned char *region = ring + (size_t)(it % R) * s.region_bytes;
+            unsigned char *region = ring + (size_t)rg2 * s.region_bytes;
+            rg2 += 2;
+            if (rg2 >= R) rg2 -= R;
             tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 1), (uint32_t)((it / T) & 1));
             tc_fence_after();
             PN2_MARK(2)
@@ -832,9 +857,10 @@ sa_tc_v3_kernel(const SaTcParams p)
         };
         auto epi3 = [&](int it) {
             const int sl = it % T;
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int bi = tile / p.tiles_per_scene;
-            const int centre0 = ((tile - bi * p.tiles_per_scene) * kTile) / NS;
+            const int bi = bi3;
+            const int centre0 = (rem3 * kTile) / NS;
+            rem3 += 2 * (int)gridDim.x;
+            while (rem3 >= p.tiles_per_scene) { rem3 -= p.tiles_per_scene; ++bi3; }
             tc_mbar_wait(bar_dfull + 8u * (sl * 3 + 2), (uint32_t)((it / T) & 1));
             tc_fence_after();
             PN2_MARK(4)
