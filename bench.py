@@ -295,23 +295,33 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
         cxyz_all.append(cxyz)
         src_xyz, table, ld, c, skip = cxyz, out_rows, out_rows.shape[2], out_rows.shape[2], 0
     known_rows = feats_rows[3]
+    from situation3d_b200._lib import lib as _pn2
     for name, (u, k), skip_rows in (("fp1", (2, 3), feats_rows[2]), ("fp2", (1, 2), feats_rows[1])):
         un, kn = cxyz_all[u], cxyz_all[k]
-        d2, i3 = fused.three_nn(un, kn)
-        t = timeit(lambda: fused.three_nn(un, kn))
-        rows.append({"kernel": "three_nn_" + name, "bound": "hbm", "seconds": t,
-                     "alg_bytes": B * (12 * (un.shape[1] + kn.shape[1]) + 24 * un.shape[1])})
         img = imgs[4 if name == "fp1" else 5]
-        run = lambda: fused.FP_FORWARD[precision](img, d2, i3, known_rows, skip_rows)
-        _, out_rows = run()
-        t = timeit(run)
         dims = img.dims
         n = un.shape[1]
         flops = 2 * B * n * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        nn_bytes = B * (12 * (un.shape[1] + kn.shape[1]) + 24 * un.shape[1])
         abytes = B * (4 * known_rows.shape[2] * kn.shape[1] + 4 * skip_rows.shape[2] * n + 24 * n + 2 * 4 * dims[-1] * n) \
             + 4 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
-        rows.append({"kernel": "%s_fused_%s" % (name, precision), "bound": "tensor", "seconds": t,
-                     "alg_flops": flops, "alg_bytes": abytes})
+        whole = lambda: fused.fp_layer(precision, img, un, kn, known_rows, skip_rows)
+        n0 = _pn2.pn2_launch_count()
+        _, out_rows = whole()
+        if _pn2.pn2_launch_count() - n0 == 1:
+            # three_nn + interpolation + concat + MLP in one launch (csrc/fp_tc2.cu)
+            t = timeit(whole)
+            rows.append({"kernel": "%s_layer_%s" % (name, precision), "bound": "tensor", "seconds": t,
+                         "alg_flops": flops, "alg_bytes": abytes + nn_bytes - 24 * B * n})
+        else:
+            d2, i3 = fused.three_nn(un, kn)
+            t = timeit(lambda: fused.three_nn(un, kn))
+            rows.append({"kernel": "three_nn_" + name, "bound": "hbm", "seconds": t, "alg_bytes": nn_bytes})
+            run = lambda: fused.FP_FORWARD[precision](img, d2, i3, known_rows, skip_rows)
+            _, out_rows = run()
+            t = timeit(run)
+            rows.append({"kernel": "%s_fused_%s" % (name, precision), "bound": "tensor", "seconds": t,
+                         "alg_flops": flops, "alg_bytes": abytes})
         known_rows = out_rows
     # share of the step: a kernel's time weighted by the fraction of the SMs its launch can occupy (the sampling kernels
     # run one CTA per scene; with several batches in flight the rest of the machine runs other batches meanwhile)

@@ -241,6 +241,18 @@ int pn2_fp_tc_forward(int b, int n, int m, int c_known, int c_skip, int c1, int 
                       const int *idx, const void *known_rows, const void *skip_rows,
                       const void *weight_image, float *out, void *out_rows, pn2_stream_t stream);
 
+/* Second-generation fused FP layer (csrc/fp_tc2.cu): three_nn (interpolate_gpu.cu:9-59 + the sqrt of
+ * pointnet2_utils.py:142) included, so it takes the coordinates instead of dist2 / idx: unknown (b,n,3), known (b,m,3)
+ * f32.  One launch per layer; a 4-CTA cluster owns a 128-point tile and splits the output channels of both MLP layers,
+ * each CTA keeping its weight quarter resident in shared memory.  Same weight image, same rows, same outputs as
+ * pn2_fp_tc_forward (bit-identical indices and weights; the bf16 rounding points are the same).
+ * Supported: c_known, c_skip multiples of 64 (c_skip may be 0), c1, c2 in {64, 128, 192, 256}, m * 12 bytes <= the
+ * operand buffer (m <= 10922 for the backbone's widths). */
+int pn2_fp_tc2_supported(int c_known, int c_skip, int c1, int c2, int m);
+int pn2_fp_tc2_forward(int b, int n, int m, int c_known, int c_skip, int c1, int c2, const float *unknown,
+                       const float *known, const void *known_rows, const void *skip_rows, const void *weight_image,
+                       float *out, void *out_rows, pn2_stream_t stream);
+
 /* ---- the linear + GELU that consumes the visual tokens (csrc/head_tc.cu) -------
  * SIG3D.scene_feat_linear = Sequential(Linear(256, 768), GELU()), situation3d/models/sqa_module.py:180-183,344:
  * out (rows, n) f32 = GELU_erf(x (rows, k) f32 . W^T + bias) as one tcgen05 kernel (bf16 operands, fp32 accumulate).
@@ -324,6 +336,15 @@ size_t pn2_project_workspace_bytes(int views, int n);
 int pn2_project(int views, int c, int hw, int n, const float *label, const long long *indices_3d,
                 const long long *indices_2d, float *out, int *status, void *workspace, size_t workspace_bytes,
                 pn2_stream_t stream);
+
+/* Across-view max-pooling of the back-projected features, the last step of the multiview-feature production: out[pt, ch]
+ * = max(0, max over views v with a correspondence for pt of label[v, ch, pixel(v, pt)]) -- the per-frame project()
+ * (lib/projection.py:257-279) folded with the running element-wise max into a zero-initialised per-point array that
+ * yields "enet_feats_maxpool" (lib/config.py:36).  Same lists and label layout as pn2_project; out is (n, c) when
+ * rows_layout != 0 (the channel-last rows the backbone reads), else (c, n).  Workspace: pn2_project_workspace_bytes. */
+int pn2_project_maxpool(int views, int c, int hw, int n, const float *label, const long long *indices_3d,
+                        const long long *indices_2d, float *out, int rows_layout, int *status, void *workspace,
+                        size_t workspace_bytes, pn2_stream_t stream);
 
 /* ---- SM partitions for callers that keep several batches in flight (csrc/sm_partition.cu) ----------
  * The sampling chain of a batch is a latency-bound kernel of half-SM CTAs that lives ~2 ms; the fused MLP

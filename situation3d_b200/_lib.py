@@ -81,6 +81,8 @@ _PROTOTYPES = {
     "pn2_fp_tc_weight_image_bytes": (c_size_t, [_i, _i, _i, _i]),
     "pn2_fp_tc_pack_weights": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "pn2_fp_tc_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_fp_tc2_supported": (_i, [_i, _i, _i, _i, _i]),
+    "pn2_fp_tc2_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_debug_sa_tc_profile": (_i, [_p]),
     "pn2_selftest_umma": (_i, [_i, _i, _p, _p, _p, _p]),
     "pn2_linear_gelu_tc_supported": (_i, [_i, _i]),
@@ -97,6 +99,7 @@ _PROTOTYPES = {
     "pn2_compute_projection": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, c_size_t, _p]),
     "pn2_project_workspace_bytes": (c_size_t, [_i, _i]),
     "pn2_project": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, c_size_t, _p]),
+    "pn2_project_maxpool": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, c_size_t, _p]),
     "pn2_quaternions_to_rotation_matrices": (_i, [_i, _p, _p, _p]),
     "pn2_rotation_vectors_to_matrices": (_i, [_i, _p, _p, _p]),
     "pn2_situation_matrices": (_i, [_i, _p, _p, _p]),

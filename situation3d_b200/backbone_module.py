@@ -148,10 +148,8 @@ class Pointnet2Backbone(nn.Module):
             data_dict["sa%d_xyz" % (lvl + 1)] = cxyz[lvl]
             data_dict["sa%d_features" % (lvl + 1)] = out
 
-        d2, i3 = _fused.three_nn(cxyz[2], cxyz[3])
-        _, fp1_rows = _fused.FP_FORWARD[self.precision](imgs[4], d2, i3, rows[3], rows[2])
-        d2, i3 = _fused.three_nn(cxyz[1], cxyz[2])
-        fp2, _ = _fused.FP_FORWARD[self.precision](imgs[5], d2, i3, fp1_rows, rows[1], want_rows=False)
+        _, fp1_rows = _fused.fp_layer(self.precision, imgs[4], cxyz[2], cxyz[3], rows[3], rows[2])
+        fp2, _ = _fused.fp_layer(self.precision, imgs[5], cxyz[1], cxyz[2], fp1_rows, rows[1], want_rows=False)
         data_dict["fp2_features"] = fp2
         data_dict["fp2_xyz"] = cxyz[1]
         data_dict["fp2_inds"] = inds[0][:, 0:cxyz[1].shape[1]]

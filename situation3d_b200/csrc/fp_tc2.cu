@@ -1,0 +1,400 @@
+// fp_tc2.cu -- feature-propagation layer, second generation: three_nn + interpolation + concat + 2-layer SharedMLP in
+// ONE launch, the output channels of both layers split over a 4-CTA cluster.
+//
+// Replaces PointnetFPModule.forward (pointnet2_modules.py:376-421) in eval mode, three_nn included
+// (interpolate_gpu.cu:9-59 + the sqrt of pointnet2_utils.py:142).  Why a second kernel: fp_tc.cu gives a 128-point tile
+// to one CTA that streams all of W1 and W2 (384 KB) through a two-stage ring -- 12 dependent load/sync/MMA steps, 32 or
+// 64 CTAs on 148 SMs, 41 us per layer for 0.2-0.4 GFLOP per scene, plus a separate three_nn launch (17-29 us).  Here
+//   * a cluster of four CTAs owns the tile; CTA r computes output channels [r*c1/4, (r+1)*c1/4) of layer 1 and
+//     [r*c2/4, (r+1)*c2/4) of layer 2, so its weight quarter (64 + 32 KB) is RESIDENT: one bulk copy, no ring;
+//   * each CTA finds the three nearest known points for a quarter of the tile's rows (8 threads per row over
+//     interleaved known points, merged lexicographically by (distance, index) = the reference's strict-'<' cascade) and
+//     posts indices and weights into all four CTAs through distributed shared memory;
+//   * every CTA builds the whole K = c_known + c_skip operand (interpolation in the reference's FMUL/FFMA/FFMA order,
+//     bf16 round) -- redundant across the cluster, but it is L2 traffic of a few hundred KB;
+//   * layer 1: 128 x c1/4 accumulators in TMEM; the bf16 activations go to ALL four CTAs' shared memory (each needs the
+//     full c1-wide A operand of layer 2) with st.shared::cluster, bracketed by cluster barriers; layer 2 likewise.
+// Four times the CTAs of fp_tc.cu, no weight streaming on the critical path, no three_nn launch.
+#include "tc_common.cuh"
+#include <math_constants.h>
+
+namespace pn2 {
+
+constexpr int kF2Tile = 128;
+constexpr int kF2Threads = 256;
+constexpr int kF2Cluster = 4;
+constexpr int kF2Slab = 64;
+
+struct Fp2Shape {
+    int c_known, c_skip, c1, c2, k0, q1, q2, nslab0, nslab1;
+    uint32_t w1_bytes, w2_bytes;            // whole-image sections (fp_tc.cu layout: W1 | W2 | bias1 | bias2)
+    uint32_t w1q_bytes, w2q_bytes, a_bytes, misc_off, smem_bytes;
+};
+
+static bool make_fp2_shape(int c_known, int c_skip, int c1, int c2, int m, Fp2Shape *s)
+{
+    if (c_known < kF2Slab || c_known % kF2Slab || c_skip < 0 || c_skip % kF2Slab) return false;
+    if (c1 < 64 || c1 > 256 || c1 % 64 || c2 < 64 || c2 > 256 || c2 % 64) return false;      // quarters: multiples of 16, <= 64
+    s->c_known = c_known; s->c_skip = c_skip; s->c1 = c1; s->c2 = c2; s->k0 = c_known + c_skip;
+    s->q1 = c1 / kF2Cluster; s->q2 = c2 / kF2Cluster;
+    s->nslab0 = s->k0 / kF2Slab; s->nslab1 = c1 / kF2Slab;
+    s->w1_bytes = kop_bytes(c1, s->k0);
+    s->w2_bytes = kop_bytes(c2, c1);
+    s->w1q_bytes = (uint32_t)s->nslab0 * s->q1 * 128u;
+    s->w2q_bytes = (uint32_t)s->nslab1 * s->q2 * 128u;
+    s->a_bytes = (uint32_t)s->nslab0 * kF2Tile * 128u;
+    // after layer 1 the A region holds: A1 (nslab1 slabs), then this CTA's W2 quarter
+    if ((uint32_t)s->nslab1 * kF2Tile * 128u + ((s->w2q_bytes + 1023u) & ~1023u) > s->a_bytes) return false;
+    if (m < 1 || (size_t)m * 12 > s->a_bytes) return false;                                  // known xyz staged in the A region
+    s->misc_off = ((s->w1q_bytes + 1023u) & ~1023u) + s->a_bytes;
+    s->smem_bytes = 1024u + s->misc_off + 4u * (s->q1 + s->q2) + kF2Tile * 24u + 64u;
+    return s->smem_bytes <= 227u * 1024u;
+}
+
+struct Fp2Params {
+    Fp2Shape s;
+    int n, m, tiles_per_scene;
+    const float *unknown, *known;
+    const __nv_bfloat16 *known_rows, *skip_rows;
+    const unsigned char *image;
+    float *out;
+    __nv_bfloat16 *out_rows;
+};
+
+__device__ __forceinline__ uint32_t f2_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void f2_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t f2_mapa(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void f2_st_cluster_v4(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void f2_st_cluster_b32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void f2_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void f2_unpack8(const uint4 &v, float (&f)[8])
+{
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 t = __bfloat1622float2(h[q]);
+        f[2 * q] = t.x; f[2 * q + 1] = t.y;
+    }
+}
+
+// (d, i) < (e, j) in the order the reference's cascade produces: smaller distance first, then the earlier index
+__device__ __forceinline__ bool nn_less(float d, int i, float e, int j) { return d < e || (d == e && i < j); }
+__device__ __forceinline__ void nn_insert(float d, int i, float (&bd)[3], int (&bi)[3])
+{
+    if (nn_less(d, i, bd[0], bi[0])) { bd[2] = bd[1]; bi[2] = bi[1]; bd[1] = bd[0]; bi[1] = bi[0]; bd[0] = d; bi[0] = i; }
+    else if (nn_less(d, i, bd[1], bi[1])) { bd[2] = bd[1]; bi[2] = bi[1]; bd[1] = d; bi[1] = i; }
+    else if (nn_less(d, i, bd[2], bi[2])) { bd[2] = d; bi[2] = i; }
+}
+
+__global__ void __cluster_dims__(kF2Cluster, 1, 1) __launch_bounds__(kF2Threads, 1)
+fp_tc2_kernel(const Fp2Params p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const Fp2Shape &s = p.s;
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    unsigned char *w1q = base;
+    unsigned char *a = base + ((s.w1q_bytes + 1023u) & ~1023u);
+    unsigned char *a1 = a;                                                    // layer-2 A operand, after layer 1
+    unsigned char *w2q = a + (size_t)s.nslab1 * kF2Tile * 128u;               // this CTA's W2 quarter, after layer 1
+    float *kxyz = reinterpret_cast<float *>(a);                               // known coordinates, before the A operand
+    float *bias1 = reinterpret_cast<float *>(base + s.misc_off);
+    float *bias2 = bias1 + s.q1;
+    int *nn_idx = reinterpret_cast<int *>(bias2 + s.q2);                      // [128][3]
+    float *nn_w = reinterpret_cast<float *>(nn_idx + kF2Tile * 3);            // [128][3]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(nn_w + kF2Tile * 3);        // w1, w2, mma1, mma2
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 4);
+    const uint32_t bar_w1 = smem_u32(mbar), bar_w2 = bar_w1 + 8, bar_m1 = bar_w1 + 16, bar_m2 = bar_w1 + 24;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = f2_ctarank();
+    const int tile = blockIdx.x / kF2Cluster;
+    const int bi = tile / p.tiles_per_scene;
+    const int row0 = (tile - bi * p.tiles_per_scene) * kF2Tile;
+
+    if (tid == 0) {
+        tc_mbar_init(bar_w1, 1); tc_mbar_init(bar_w2, 1); tc_mbar_init(bar_m1, 1); tc_mbar_init(bar_m2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<128>(smem_u32(tmem_slot));
+    {
+        const float *bsrc = reinterpret_cast<const float *>(p.image + s.w1_bytes + s.w2_bytes);
+        for (int i = tid; i < s.q1; i += kF2Threads) bias1[i] = __ldg(bsrc + rank * s.q1 + i);
+        for (int i = tid; i < s.q2; i += kF2Threads) bias2[i] = __ldg(bsrc + s.c1 + rank * s.q2 + i);
+        const float *kn = p.known + (size_t)bi * p.m * 3;
+        for (int i = tid; i < p.m * 3; i += kF2Threads) kxyz[i] = __ldg(kn + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) {
+        // this CTA's quarter of W1: rows [rank*q1, +q1) of every 64-column tile of the image are contiguous
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w1), "r"(s.w1q_bytes) : "memory");
+        for (int t = 0; t < s.nslab0; ++t)
+            f2_bulk_load(smem_u32(w1q) + (uint32_t)t * s.q1 * 128u, p.image + (size_t)t * s.c1 * 128u + (size_t)rank * s.q1 * 128u,
+                         (uint32_t)s.q1 * 128u, bar_w1);
+    }
+    f2_cluster_sync();        // every CTA's barriers and buffers exist before anyone posts into them
+
+    // ---- three nearest known points for rows [32*rank, 32*rank + 32) of the tile: 8 threads per row ----------------
+    {
+        const int lr = tid >> 3, sub = tid & 7;                     // local row 0..31, slice of the known points
+        const int trow = (int)rank * 32 + lr, row = row0 + trow;
+        float bd[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};   // interpolate_gpu.cu:27: best = 1e40 (double) -> inf as float
+        int bj[3] = {0, 0, 0};
+        if (row < p.n) {
+            const float *u = p.unknown + ((size_t)bi * p.n + row) * 3;
+            const float ux = __ldg(u), uy = __ldg(u + 1), uz = __ldg(u + 2);
+            for (int j = sub; j < p.m; j += 8) {
+                const float d = sqdist3_yxz(ux, uy, uz, kxyz[3 * j], kxyz[3 * j + 1], kxyz[3 * j + 2]);
+                // strict '<' against the running bests in index order (interpolate_gpu.cu:33-47); NaN never enters
+                if (d < bd[0]) { bd[2] = bd[1]; bj[2] = bj[1]; bd[1] = bd[0]; bj[1] = bj[0]; bd[0] = d; bj[0] = j; }
+                else if (d < bd[1]) { bd[2] = bd[1]; bj[2] = bj[1]; bd[1] = d; bj[1] = j; }
+                else if (d < bd[2]) { bd[2] = d; bj[2] = j; }
+            }
+        }
+        // merge the 8 slices: (distance, index) lexicographic = what one thread scanning 0..m-1 would keep.  Slots that
+        // were never filled are (inf, 0); a filled slot always has a finite or equal distance and wins or ties correctly
+        // because an unfilled slot can only survive when fewer than three points exist at all.
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            float od[3]; int oj[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { od[k] = __shfl_xor_sync(0xffffffffu, bd[k], o); oj[k] = __shfl_xor_sync(0xffffffffu, bj[k], o); }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (od[k] < CUDART_INF_F) nn_insert(od[k], oj[k], bd, bj);
+        }
+        if (sub == 0) {
+            float w[3] = {0.f, 0.f, 0.f};
+            if (row < p.n) {
+                // pointnet2_utils.py:142 sqrt; pointnet2_modules.py:399-402 1/(d + 1e-8), normalise
+                const float d1 = __fsqrt_rn(bd[0]), d2 = __fsqrt_rn(bd[1]), d3 = __fsqrt_rn(bd[2]);
+                const float r1 = __fdiv_rn(1.0f, __fadd_rn(d1, 1e-8f)), r2 = __fdiv_rn(1.0f, __fadd_rn(d2, 1e-8f)),
+                            r3 = __fdiv_rn(1.0f, __fadd_rn(d3, 1e-8f));
+                const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+                w[0] = __fdiv_rn(r1, norm); w[1] = __fdiv_rn(r2, norm); w[2] = __fdiv_rn(r3, norm);
+            }
+            const uint32_t ia = smem_u32(nn_idx + trow * 3), wa = smem_u32(nn_w + trow * 3);
+#pragma unroll
+            for (uint32_t c = 0; c < kF2Cluster; ++c) {
+                const uint32_t ra = f2_mapa(ia, c), rw = f2_mapa(wa, c);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { f2_st_cluster_b32(ra + 4 * k, (uint32_t)bj[k]); f2_st_cluster_b32(rw + 4 * k, __float_as_uint(w[k])); }
+            }
+        }
+    }
+    f2_cluster_sync();        // indices / weights of all 128 rows are here; the known coordinates are dead
+
+    // ---- the K = c_known + c_skip operand: thread -> row tid % 128, slabs of parity tid / 128 ---------------------
+    {
+        const int r = tid & 127, half = tid >> 7;
+        const int row = row0 + r;
+        const bool valid = row < p.n;
+        const float w1 = nn_w[r * 3], w2 = nn_w[r * 3 + 1], w3 = nn_w[r * 3 + 2];
+        const __nv_bfloat16 *kr = p.known_rows + (size_t)bi * p.m * s.c_known;
+        const __nv_bfloat16 *f1 = kr + (size_t)nn_idx[r * 3] * s.c_known, *f2 = kr + (size_t)nn_idx[r * 3 + 1] * s.c_known,
+                            *f3 = kr + (size_t)nn_idx[r * 3 + 2] * s.c_known;
+        const __nv_bfloat16 *sk = p.skip_rows + ((size_t)bi * p.n + (valid ? row : 0)) * s.c_skip;
+        const int nk = s.c_known / kF2Slab;
+        for (int kb = half; kb < s.nslab0; kb += 2) {
+            unsigned char *dst = a + (size_t)kb * kF2Tile * 128u + r * 128;
+            if (kb < nk) {
+                uint4 va[8], vb[8], vc[8];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    va[ch] = vb[ch] = vc[ch] = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) {
+                        va[ch] = __ldg(reinterpret_cast<const uint4 *>(f1 + kb * kF2Slab) + ch);
+                        vb[ch] = __ldg(reinterpret_cast<const uint4 *>(f2 + kb * kF2Slab) + ch);
+                        vc[ch] = __ldg(reinterpret_cast<const uint4 *>(f3 + kb * kF2Slab) + ch);
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    float fa[8], fb[8], fc[8];
+                    f2_unpack8(va[ch], fa); f2_unpack8(vb[ch], fb); f2_unpack8(vc[ch], fc);
+                    uint32_t o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)          // interpolate_gpu.cu:90-99 in its FMUL/FFMA/FFMA order (common.cuh)
+                        o[q] = pack_bf16(interp3(fa[2 * q], w1, fb[2 * q], w2, fc[2 * q], w3),
+                                         interp3(fa[2 * q + 1], w1, fb[2 * q + 1], w2, fc[2 * q + 1], w3));
+                    *reinterpret_cast<uint4 *>(dst + ((ch ^ (r & 7)) << 4)) = valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            } else {
+                const __nv_bfloat16 *src = sk + (kb - nk) * kF2Slab;
+                uint4 v[8];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) v[ch] = valid ? __ldg(reinterpret_cast<const uint4 *>(src) + ch) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4 *>(dst + ((ch ^ (r & 7)) << 4)) = v[ch];
+            }
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- layer 1: D1[128][q1] = A[128][k0] W1q[q1][k0]^T ------------------------------------------------------------
+    if (warp == 0) {
+        tc_mbar_wait(bar_w1, 0);
+        tc_fence_after();
+        const uint32_t elected = elect_one();
+        const uint32_t idesc = umma_idesc(kF2Tile, s.q1);
+        for (int kb = 0; kb < s.nslab0; ++kb) {
+            const uint64_t da = smem_desc(smem_u32(a) + (uint32_t)kb * (kF2Tile * 128u), 1024u, kSw128);
+            const uint64_t db = smem_desc(smem_u32(w1q) + (uint32_t)kb * (uint32_t)s.q1 * 128u, 1024u, kSw128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                if (elected) umma_bf16(tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+        }
+        if (elected) umma_commit(bar_m1);
+        __syncwarp();
+    }
+    tc_mbar_wait(bar_m1, 0);
+    tc_fence_after();
+    if (tid == 0) {
+        // the A operand is dead in THIS CTA: fetch the W2 quarter into its tail (behind the A1 area the cluster fills)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w2), "r"(s.w2q_bytes) : "memory");
+        for (int t = 0; t < s.nslab1; ++t)
+            f2_bulk_load(smem_u32(w2q) + (uint32_t)t * s.q2 * 128u,
+                         p.image + s.w1_bytes + (size_t)t * s.c2 * 128u + (size_t)rank * s.q2 * 128u, (uint32_t)s.q2 * 128u, bar_w2);
+    }
+    f2_cluster_sync();        // every CTA has finished reading ITS A operand: the A1 areas may be overwritten
+
+    // ---- epilogue 1: + bias, ReLU, bf16 -> columns [rank*q1, +q1) of the A1 operand of all four CTAs ----------------
+    if (warp < 4) {
+        const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+        const int r = tid;
+        for (int c0 = 0; c0 < s.q1; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(my_tmem + c0, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t o[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int j = q * 8 + h * 2;
+                    o[h] = pack_bf16(fmaxf(__uint_as_float(v[j]) + bias1[c0 + j], 0.f), fmaxf(__uint_as_float(v[j + 1]) + bias1[c0 + j + 1], 0.f));
+                }
+                const int cabs = (int)rank * s.q1 + c0 + q * 8;                      // first of the 8 channels of this chunk
+                const uint32_t off = (uint32_t)(cabs >> 6) * (kF2Tile * 128u) + (uint32_t)r * 128u + ((((uint32_t)(cabs & 63) >> 3) ^ ((uint32_t)r & 7u)) << 4);
+                const uint32_t la = smem_u32(a1) + off;
+#pragma unroll
+                for (uint32_t c = 0; c < kF2Cluster; ++c) f2_st_cluster_v4(f2_mapa(la, c), make_uint4(o[0], o[1], o[2], o[3]));
+            }
+        }
+        tc_fence_before();
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    f2_cluster_sync();        // all four quarters of A1 have landed everywhere
+    fence_proxy_async();
+
+    // ---- layer 2: D2[128][q2] = A1[128][c1] W2q[q2][c1]^T -------------------------------------------------------------
+    if (warp == 0) {
+        tc_mbar_wait(bar_w2, 0);
+        tc_fence_after();
+        const uint32_t elected = elect_one();
+        const uint32_t idesc = umma_idesc(kF2Tile, s.q2);
+        for (int kb = 0; kb < s.nslab1; ++kb) {
+            const uint64_t da = smem_desc(smem_u32(a1) + (uint32_t)kb * (kF2Tile * 128u), 1024u, kSw128);
+            const uint64_t db = smem_desc(smem_u32(w2q) + (uint32_t)kb * (uint32_t)s.q2 * 128u, 1024u, kSw128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                if (elected) umma_bf16(tmem + 64, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+        }
+        if (elected) umma_commit(bar_m2);
+        __syncwarp();
+    }
+    tc_mbar_wait(bar_m2, 0);
+    tc_fence_after();
+
+    // ---- epilogue 2: + bias, ReLU -> (B, c2, n) fp32 and the bf16 rows the next layer reads ---------------------------
+    if (warp < 4) {
+        const uint32_t my_tmem = tmem + 64 + ((uint32_t)(warp * 32) << 16);
+        const int row = row0 + tid;
+        const bool valid = row < p.n;
+        for (int c0 = 0; c0 < s.q2; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(my_tmem + c0, v);
+            if (valid) {
+                const int cb = (int)rank * s.q2 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float o = fmaxf(__uint_as_float(v[j]) + bias2[c0 + j], 0.f);
+                    p.out[((size_t)bi * s.c2 + cb + j) * p.n + row] = o;               // coalesced over the warp's points
+                    v[j] = __float_as_uint(o);
+                }
+                if (p.out_rows) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(p.out_rows + ((size_t)bi * p.n + row) * s.c2 + cb);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        dst[q] = make_uint4(pack_bf16(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])),
+                                            pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                                            pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                                            pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_fp_tc2_supported(int c_known, int c_skip, int c1, int c2, int m)
+{
+    Fp2Shape s;
+    return make_fp2_shape(c_known, c_skip, c1, c2, m, &s) ? 1 : 0;
+}
+
+extern "C" int pn2_fp_tc2_forward(int b, int n, int m, int c_known, int c_skip, int c1, int c2, const float *unknown,
+                                  const float *known, const void *known_rows, const void *skip_rows, const void *weight_image,
+                                  float *out, void *out_rows, pn2_stream_t stream)
+{
+    Fp2Params p;
+    if (b < 0 || n < 0 || !make_fp2_shape(c_known, c_skip, c1, c2, m, &p.s)) return PN2_ERR_INVALID_ARGUMENT;
+    if (b == 0 || n == 0) return PN2_OK;
+    if (!unknown || !known || !known_rows || (c_skip > 0 && !skip_rows) || !weight_image || !out) return PN2_ERR_INVALID_ARGUMENT;
+    p.n = n; p.m = m;
+    p.tiles_per_scene = ceil_div(n, kF2Tile);
+    p.unknown = unknown; p.known = known;
+    p.known_rows = static_cast<const __nv_bfloat16 *>(known_rows);
+    p.skip_rows = static_cast<const __nv_bfloat16 *>(c_skip > 0 ? skip_rows : known_rows);
+    p.image = static_cast<const unsigned char *>(weight_image);
+    p.out = out;
+    p.out_rows = static_cast<__nv_bfloat16 *>(out_rows);
+    const long long ctas = (long long)b * p.tiles_per_scene * kF2Cluster;
+    if (ctas > 0x7fffffffLL) return PN2_ERR_INVALID_ARGUMENT;
+    PN2_CUDA_TRY(cudaFuncSetAttribute(fp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.s.smem_bytes));
+    fp_tc2_kernel<<<(unsigned)ctas, kF2Threads, p.s.smem_bytes, as_stream(stream)>>>(p);
+    PN2_LAUNCH_CHECK("fp_tc2_forward");
+    return PN2_OK;
+}

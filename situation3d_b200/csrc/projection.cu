@@ -343,6 +343,43 @@ extern "C" int pn2_compute_projection(int views, int n, const float *points, con
     return PN2_OK;
 }
 
+// Across-view pooling of the back-projected features: out[pt, ch] = max(0, max over the views v that see point pt of
+// label[v, ch, pixmap[v, pt]]) -- the running element-wise max over frames that produces the 128-d multiview input
+// ("enet_feats_maxpool", lib/config.py:36; per frame: ProjectionHelper.project, lib/projection.py:257-279, into a
+// zero-initialised per-point array).  One thread per point and CPB channels in registers; the (views, c, n) tensor that
+// project() materialises per frame (1.6 GB for 64 views x 128 channels x 50 000 points) is never written.
+template <int CPB>
+__global__ void __launch_bounds__(kProjThreads)
+project_maxpool_kernel(int views, int n, int c, int hw, const int *__restrict__ pixmap, const float *__restrict__ label,
+                       float *__restrict__ out, int rows_layout)
+{
+    const int c0 = blockIdx.y * CPB;
+    const int pt = blockIdx.x * kProjThreads + threadIdx.x;
+    if (pt >= n) return;
+    const int nc = min(CPB, c - c0);
+    float acc[CPB];
+#pragma unroll
+    for (int j = 0; j < CPB; ++j) acc[j] = 0.f;
+    for (int v = 0; v < views; ++v) {
+        const int pix = pixmap[(size_t)v * n + pt];
+        if (pix < 0) continue;
+        const float *lab = label + ((size_t)v * c + c0) * hw + pix;
+#pragma unroll
+        for (int j = 0; j < CPB; ++j)
+            if (j < nc) acc[j] = fmaxf(acc[j], __ldg(lab + (size_t)j * hw));
+    }
+    if (rows_layout) {
+        float *o = out + (size_t)pt * c + c0;
+#pragma unroll
+        for (int j = 0; j < CPB; ++j)
+            if (j < nc) o[j] = acc[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPB; ++j)
+            if (j < nc) out[(size_t)(c0 + j) * n + pt] = acc[j];
+    }
+}
+
 extern "C" size_t pn2_project_workspace_bytes(int views, int n)
 {
     if (views < 0 || n < 0) return 0;
@@ -370,5 +407,30 @@ extern "C" int pn2_project(int views, int c, int hw, int n, const float *label, 
     //  64 views x 128 channels x 50 000 points: nearly every warp then holds a correspondence and runs the gather path)
     project_dense_kernel<kCpb><<<dim3(blocks, ceil_div(c, kCpb), views), kProjThreads, 0, as_stream(stream)>>>(n, c, hw, pixmap, label, out);
     PN2_LAUNCH_CHECK("project_dense");
+    return PN2_OK;
+}
+
+extern "C" int pn2_project_maxpool(int views, int c, int hw, int n, const float *label, const long long *indices_3d,
+                                   const long long *indices_2d, float *out, int rows_layout, int *status, void *workspace,
+                                   size_t workspace_bytes, pn2_stream_t stream)
+{
+    if (views < 0 || c < 1 || hw < 1 || n < 0 || !status) return PN2_ERR_INVALID_ARGUMENT;
+    PN2_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), as_stream(stream)));
+    if (n == 0) return PN2_OK;
+    if (views > 65535 || !out || (views > 0 && (!label || !indices_3d || !indices_2d))) return PN2_ERR_INVALID_ARGUMENT;
+    if (views > 0 && (!workspace || workspace_bytes < pn2_project_workspace_bytes(views, n))) return PN2_ERR_WORKSPACE;
+    int *pixmap = static_cast<int *>(workspace);
+    const int blocks = ceil_div(n, kProjThreads);
+    if (views > 0) {
+        PN2_CUDA_TRY(cudaMemsetAsync(pixmap, 0xff, sizeof(int) * (size_t)views * n, as_stream(stream)));
+        project_map_kernel<<<dim3(blocks < 64 ? blocks : 64, views), kProjThreads, 0, as_stream(stream)>>>(n, hw, indices_3d,
+                                                                                                           indices_2d, pixmap, status);
+        PN2_LAUNCH_CHECK("project_map");
+    }
+    constexpr int kCpb = 16;
+    if (ceil_div(c, kCpb) > 65535) return PN2_ERR_INVALID_ARGUMENT;
+    project_maxpool_kernel<kCpb><<<dim3(blocks, ceil_div(c, kCpb)), kProjThreads, 0, as_stream(stream)>>>(views, n, c, hw, pixmap, label,
+                                                                                                        out, rows_layout ? 1 : 0);
+    PN2_LAUNCH_CHECK("project_maxpool");
     return PN2_OK;
 }

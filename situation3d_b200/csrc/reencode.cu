@@ -158,11 +158,37 @@ reencode_v2_kernel(int b, int t, int h, int mode, const float *__restrict__ toke
     float *hid = w2t + (size_t)h * D;            // [h][kTok2]
     float *pxy = hid + (size_t)h * kTok2;        // [kTok2][2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // W2 (D, h) row-major -> W2T[h][D]: lanes take consecutive outputs (conflict-free stores; the strided global reads
-    // come out of L2 once per CTA)
-    for (int i = tid; i < h * D; i += kReThreads) {
-        const int dd = i % D, hh = i / D;
-        w2t[hh * D + dd] = __ldg(w2 + (size_t)dd * h + hh);
+    // W2 (D, h) row-major -> W2T[h][D].  A warp takes 32 consecutive outputs dd and one 16-byte piece of their rows:
+    // the shared-memory stores are conflict-free (consecutive dd), the global reads use half of every 32-byte sector
+    // (out of L2, once per CTA); eight independent loads are in flight per thread.
+    if ((h & 3) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0) {
+        const int pieces = h / 4, total = (D / 32) * pieces;          // (dd block, piece) items per warp-iteration
+        for (int it0 = warp; it0 < total; it0 += 8 * (kReThreads / 32)) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int it = it0 + u * (kReThreads / 32);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it < total) {
+                    const int dblk = it / pieces, pc = it - dblk * pieces;
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(w2 + (size_t)(dblk * 32 + lane) * h) + pc);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int it = it0 + u * (kReThreads / 32);
+                if (it < total) {
+                    const int dblk = it / pieces, pc = it - dblk * pieces;
+                    float *dst = w2t + (size_t)(4 * pc) * D + dblk * 32 + lane;
+                    dst[0] = v[u].x; dst[D] = v[u].y; dst[2 * D] = v[u].z; dst[3 * D] = v[u].w;
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < h * D; i += kReThreads) {
+            const int dd = i % D, hh = i / D;
+            w2t[hh * D + dd] = __ldg(w2 + (size_t)dd * h + hh);
+        }
     }
     const float4 bias_lo = __ldg(reinterpret_cast<const float4 *>(b2) + lane);
     const float4 bias_hi = __ldg(reinterpret_cast<const float4 *>(b2 + 128) + lane);

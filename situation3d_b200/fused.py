@@ -413,5 +413,31 @@ def fp_forward_bf16(img, dist2, idx, known_rows, skip_rows, want_rows=True):
     return out, out_rows
 
 
+def fp_layer(precision, img, unknown, known, known_rows, skip_rows, want_rows=True):
+    """One whole feature-propagation layer from coordinates: three_nn + interpolation + concat + SharedMLP.  The bf16
+    arm runs it as ONE launch (pn2_fp_tc2_forward: 4-CTA clusters, resident weight quarters) when the shapes allow;
+    otherwise three_nn followed by the fused MLP kernel of the precision."""
+    import os
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    dims = img.dims
+    if precision == "bf16" and not img.f32_only and len(dims) == 3 and os.environ.get("PN2_FP_TC2", "1") != "0":
+        c_known = known_rows.shape[2]
+        c_skip = 0 if skip_rows is None else skip_rows.shape[2]
+        if known_rows.dtype == torch.bfloat16 and (skip_rows is None or skip_rows.dtype == torch.bfloat16) and \
+                lib.pn2_fp_tc2_supported(c_known, c_skip, dims[1], dims[2], m):
+            known_rows = known_rows.contiguous()
+            skip_rows = None if skip_rows is None else skip_rows.contiguous()
+            out = torch.empty((B, dims[2], n), dtype=torch.float32, device=unknown.device)
+            out_rows = torch.empty((B, n, dims[2]), dtype=torch.bfloat16, device=unknown.device) if want_rows else None
+            with torch.cuda.device(unknown.device):
+                check(lib.pn2_fp_tc2_forward(B, n, m, c_known, c_skip, dims[1], dims[2], ptr(unknown), ptr(known),
+                                             ptr(known_rows), ptr(skip_rows), ptr(img.image), ptr(out), ptr(out_rows),
+                                             stream_ptr()), "fp_tc2_forward")
+            return out, out_rows
+    dist2, idx = three_nn(unknown, known)
+    return FP_FORWARD[precision](img, dist2, idx, known_rows, skip_rows, want_rows)
+
+
 SA_FORWARD = {"fp32": sa_forward_f32, "bf16": sa_forward_bf16}
 FP_FORWARD = {"fp32": fp_forward_f32, "bf16": fp_forward_bf16}

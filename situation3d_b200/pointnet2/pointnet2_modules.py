@@ -244,8 +244,7 @@ class PointnetFPModule(nn.Module):
         Returns (out (B,cout,n), out_rows (B,n,cout))."""
         if img is None:
             img = self._fused_image(unknown)
-        dist2, idx = _fused.three_nn(unknown, known)
-        return _fused.FP_FORWARD[self.precision](img, dist2, idx, known_rows, skip_rows)
+        return _fused.fp_layer(self.precision, img, unknown, known, known_rows, skip_rows)
 
     def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
                 known_feats: torch.Tensor) -> torch.Tensor:

@@ -44,6 +44,36 @@ def project_views(label, lin_indices_3d, lin_indices_2d, num_points):
     return out
 
 
+@torch.no_grad()
+def project_views_maxpool(label, lin_indices_3d, lin_indices_2d, num_points, layout="rows"):
+    """The multiview feature of every point: max over the views that see it of the back-projected image feature, 0 where
+    no view does -- ``project`` of every frame (lib/projection.py:257-279) folded with the running element-wise max into a
+    zero-initialised per-point array (the "enet_feats_maxpool" input, lib/config.py:36) in one pass, without the
+    (V, C, num_points) intermediate.  label (V,C,H,W) or (V,C,HW); lists (V,num_points+1).
+    Returns (num_points, C) for ``layout="rows"`` (the channel-last rows the backbone reads) or (C, num_points)."""
+    if not (label.is_cuda and lin_indices_3d.is_cuda and lin_indices_2d.is_cuda):
+        raise RuntimeError("ProjectionHelper: CUDA tensors required (there is no CPU path)")
+    if layout not in ("rows", "channels"):
+        raise ValueError("layout must be 'rows' or 'channels'")
+    V, C = label.shape[0], label.shape[1]
+    label = label.to(torch.float32).reshape(V, C, -1).contiguous()
+    i3 = lin_indices_3d.to(torch.int64).reshape(V, -1).contiguous()
+    i2 = lin_indices_2d.to(torch.int64).reshape(V, -1).contiguous()
+    if V > 0 and (i3.shape[1] != num_points + 1 or i2.shape[1] != num_points + 1):
+        raise RuntimeError("ProjectionHelper.project: index lists must have num_points + 1 entries")
+    dev = label.device
+    out = torch.empty((num_points, C) if layout == "rows" else (C, num_points), dtype=torch.float32, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = lib.pn2_project_workspace_bytes(V, num_points)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.pn2_project_maxpool(V, C, label.shape[2], num_points, ptr(label), ptr(i3), ptr(i2), ptr(out),
+                                      1 if layout == "rows" else 0, ptr(status), ptr(ws), nbytes, stream_ptr()), "project_maxpool")
+    if int(status.item()) != 0:
+        raise IndexError("ProjectionHelper.project: index out of range")
+    return out
+
+
 class ProjectionHelper:
     def __init__(self, intrinsic, depth_min, depth_max, image_dims, accuracy, cuda=True):
         if not cuda:
@@ -170,6 +200,10 @@ class ProjectionHelper:
         return project_views(label, lin_indices_3d, lin_indices_2d, num_points)
 
     @torch.no_grad()
+    def project_views_maxpool(self, label, lin_indices_3d, lin_indices_2d, num_points, layout="rows"):
+        """All views -> the max-pooled multiview feature of every point (see the module-level function)."""
+        return project_views_maxpool(label, lin_indices_3d, lin_indices_2d, num_points, layout)
+
     def project(self, label, lin_indices_3d, lin_indices_2d, num_points):
         """One view, the reference's signature (lib/projection.py:257-279): label (C,H,W) or (H,W) -> (C,num_points)."""
         c = 1 if label.dim() == 2 else label.shape[0]
