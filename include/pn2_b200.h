@@ -253,6 +253,10 @@ int pn2_fp_tc2_forward(int b, int n, int m, int c_known, int c_skip, int c1, int
                        const float *known, const void *known_rows, const void *skip_rows, const void *weight_image,
                        float *out, void *out_rows, pn2_stream_t stream);
 
+/* Diagnostic: while prof (device, 16 x int64) is non-NULL, pn2_fp_tc2_forward records the SM clock of thread 0 of
+ * CTA 0 at its phase boundaries (csrc/fp_tc2.cu). */
+int pn2_debug_fp_tc2_profile(long long *prof);
+
 /* ---- the linear + GELU that consumes the visual tokens (csrc/head_tc.cu) -------
  * SIG3D.scene_feat_linear = Sequential(Linear(256, 768), GELU()), situation3d/models/sqa_module.py:180-183,344:
  * out (rows, n) f32 = GELU_erf(x (rows, k) f32 . W^T + bias) as one tcgen05 kernel (bf16 operands, fp32 accumulate).

@@ -83,6 +83,7 @@ _PROTOTYPES = {
     "pn2_fp_tc_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_fp_tc2_supported": (_i, [_i, _i, _i, _i, _i]),
     "pn2_fp_tc2_forward": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_debug_fp_tc2_profile": (_i, [_p]),
     "pn2_debug_sa_tc_profile": (_i, [_p]),
     "pn2_selftest_umma": (_i, [_i, _i, _p, _p, _p, _p]),
     "pn2_linear_gelu_tc_supported": (_i, [_i, _i]),

@@ -59,6 +59,7 @@ struct Fp2Params {
     const unsigned char *image;
     float *out;
     __nv_bfloat16 *out_rows;
+    long long *prof;        // diagnostic: SM clock of thread 0 of CTA 0 at the phase boundaries (NULL = off)
 };
 
 __device__ __forceinline__ uint32_t f2_ctarank()
@@ -129,8 +130,12 @@ fp_tc2_kernel(const Fp2Params p)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 4);
     const uint32_t bar_w1 = smem_u32(mbar), bar_w2 = bar_w1 + 8, bar_m1 = bar_w1 + 16, bar_m2 = bar_w1 + 24;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t rank = f2_ctarank();
+    const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    int pslot = 0;
+#define PN2_FP2_MARK() if (profiling) p.prof[pslot++] = clock64();
+    PN2_FP2_MARK()
     const int tile = blockIdx.x / kF2Cluster;
     const int bi = tile / p.tiles_per_scene;
     const int row0 = (tile - bi * p.tiles_per_scene) * kF2Tile;
@@ -154,11 +159,16 @@ fp_tc2_kernel(const Fp2Params p)
     if (tid == 0) {
         // this CTA's quarter of W1: rows [rank*q1, +q1) of every 64-column tile of the image are contiguous
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w1), "r"(s.w1q_bytes) : "memory");
-        for (int t = 0; t < s.nslab0; ++t)
+        // (every cluster reads the same 384 KB of weights: start at a different slab per tile so that the clusters of a
+        //  wave do not all pull the same L2 lines at the same moment)
+        for (int i = 0; i < s.nslab0; ++i) {
+            const int t = (i + tile) % s.nslab0;
             f2_bulk_load(smem_u32(w1q) + (uint32_t)t * s.q1 * 128u, p.image + (size_t)t * s.c1 * 128u + (size_t)rank * s.q1 * 128u,
                          (uint32_t)s.q1 * 128u, bar_w1);
+        }
     }
     f2_cluster_sync();        // every CTA's barriers and buffers exist before anyone posts into them
+    PN2_FP2_MARK()
 
     // ---- three nearest known points for rows [32*rank, 32*rank + 32) of the tile: 8 threads per row ----------------
     {
@@ -171,10 +181,12 @@ fp_tc2_kernel(const Fp2Params p)
             const float ux = __ldg(u), uy = __ldg(u + 1), uz = __ldg(u + 2);
             for (int j = sub; j < p.m; j += 8) {
                 const float d = sqdist3_yxz(ux, uy, uz, kxyz[3 * j], kxyz[3 * j + 1], kxyz[3 * j + 2]);
-                // strict '<' against the running bests in index order (interpolate_gpu.cu:33-47); NaN never enters
-                if (d < bd[0]) { bd[2] = bd[1]; bj[2] = bj[1]; bd[1] = bd[0]; bj[1] = bj[0]; bd[0] = d; bj[0] = j; }
-                else if (d < bd[1]) { bd[2] = bd[1]; bj[2] = bj[1]; bd[1] = d; bj[1] = j; }
-                else if (d < bd[2]) { bd[2] = d; bj[2] = j; }
+                // strict '<' against the running bests in index order (interpolate_gpu.cu:33-47), as selects (the three-way
+                // branch diverges across the rows of a warp); NaN never enters
+                const bool c0 = d < bd[0], c1 = d < bd[1], c2 = d < bd[2];
+                bd[2] = c1 ? bd[1] : (c2 ? d : bd[2]); bj[2] = c1 ? bj[1] : (c2 ? j : bj[2]);
+                bd[1] = c0 ? bd[0] : (c1 ? d : bd[1]); bj[1] = c0 ? bj[0] : (c1 ? j : bj[1]);
+                bd[0] = c0 ? d : bd[0];                bj[0] = c0 ? j : bj[0];
             }
         }
         // merge the 8 slices: (distance, index) lexicographic = what one thread scanning 0..m-1 would keep.  Slots that
@@ -208,55 +220,78 @@ fp_tc2_kernel(const Fp2Params p)
             }
         }
     }
+    PN2_FP2_MARK()
     f2_cluster_sync();        // indices / weights of all 128 rows are here; the known coordinates are dead
+    PN2_FP2_MARK()
 
-    // ---- the K = c_known + c_skip operand: thread -> row tid % 128, slabs of parity tid / 128 ---------------------
+    // ---- the K = c_known + c_skip operand.  Eight lanes share a row (one 16-byte piece of a 64-channel slab each), so a
+    // warp instruction reads four whole 128-byte row pieces instead of 16 bytes out of 32 different rows; warp w builds
+    // rows 16w .. 16w+15, four at a time.
     {
-        const int r = tid & 127, half = tid >> 7;
-        const int row = row0 + r;
-        const bool valid = row < p.n;
-        const float w1 = nn_w[r * 3], w2 = nn_w[r * 3 + 1], w3 = nn_w[r * 3 + 2];
-        const __nv_bfloat16 *kr = p.known_rows + (size_t)bi * p.m * s.c_known;
-        const __nv_bfloat16 *f1 = kr + (size_t)nn_idx[r * 3] * s.c_known, *f2 = kr + (size_t)nn_idx[r * 3 + 1] * s.c_known,
-                            *f3 = kr + (size_t)nn_idx[r * 3 + 2] * s.c_known;
-        const __nv_bfloat16 *sk = p.skip_rows + ((size_t)bi * p.n + (valid ? row : 0)) * s.c_skip;
+        const int lane = tid & 31, piece = lane & 7, rsub = lane >> 3;
         const int nk = s.c_known / kF2Slab;
-        for (int kb = half; kb < s.nslab0; kb += 2) {
-            unsigned char *dst = a + (size_t)kb * kF2Tile * 128u + r * 128;
-            if (kb < nk) {
-                uint4 va[8], vb[8], vc[8];
+        const __nv_bfloat16 *kr = p.known_rows + (size_t)bi * p.m * s.c_known;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+            const int r = warp * 16 + g * 4 + rsub;
+            const int row = row0 + r;
+            const bool valid = row < p.n;
+            const float w1 = nn_w[r * 3], w2 = nn_w[r * 3 + 1], w3 = nn_w[r * 3 + 2];
+            const __nv_bfloat16 *f1 = kr + (size_t)nn_idx[r * 3] * s.c_known + piece * 8,
+                                *f2 = kr + (size_t)nn_idx[r * 3 + 1] * s.c_known + piece * 8,
+                                *f3 = kr + (size_t)nn_idx[r * 3 + 2] * s.c_known + piece * 8;
+            const __nv_bfloat16 *sk = p.skip_rows + ((size_t)bi * p.n + (valid ? row : 0)) * s.c_skip + piece * 8;
+            unsigned char *dst = a + r * 128 + ((piece ^ (r & 7)) << 4);
+            // all of a row's pieces are requested before the first is used: one memory round trip per group of rows
+            constexpr int kMaxSlab = 8;
+            uint4 va[kMaxSlab], vb[kMaxSlab / 2], vc[kMaxSlab / 2];
+            for (int kb0 = 0; kb0 < s.nslab0; kb0 += kMaxSlab) {
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    va[ch] = vb[ch] = vc[ch] = make_uint4(0u, 0u, 0u, 0u);
-                    if (valid) {
-                        va[ch] = __ldg(reinterpret_cast<const uint4 *>(f1 + kb * kF2Slab) + ch);
-                        vb[ch] = __ldg(reinterpret_cast<const uint4 *>(f2 + kb * kF2Slab) + ch);
-                        vc[ch] = __ldg(reinterpret_cast<const uint4 *>(f3 + kb * kF2Slab) + ch);
+                for (int u = 0; u < kMaxSlab; ++u) {
+                    const int kb = kb0 + u;
+                    va[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (u < kMaxSlab / 2) vb[u] = vc[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid && kb < s.nslab0) {
+                        if (kb < nk) {
+                            va[u] = __ldg(reinterpret_cast<const uint4 *>(f1 + kb * kF2Slab));
+                            if (u < kMaxSlab / 2) {
+                                vb[u] = __ldg(reinterpret_cast<const uint4 *>(f2 + kb * kF2Slab));
+                                vc[u] = __ldg(reinterpret_cast<const uint4 *>(f3 + kb * kF2Slab));
+                            }
+                        } else {
+                            va[u] = __ldg(reinterpret_cast<const uint4 *>(sk + (kb - nk) * kF2Slab));
+                        }
                     }
                 }
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    float fa[8], fb[8], fc[8];
-                    f2_unpack8(va[ch], fa); f2_unpack8(vb[ch], fb); f2_unpack8(vc[ch], fc);
-                    uint32_t o[4];
+                for (int u = 0; u < kMaxSlab; ++u) {
+                    const int kb = kb0 + u;
+                    if (kb >= s.nslab0) break;
+                    uint4 o = va[u];
+                    if (kb < nk) {
+                        uint4 b4 = make_uint4(0u, 0u, 0u, 0u), c4 = b4;
+                        if (u < kMaxSlab / 2) { b4 = vb[u]; c4 = vc[u]; }
+                        else if (valid) {       // more than four interpolated slabs in this pass (c_known > 256): fetched late
+                            b4 = __ldg(reinterpret_cast<const uint4 *>(f2 + kb * kF2Slab));
+                            c4 = __ldg(reinterpret_cast<const uint4 *>(f3 + kb * kF2Slab));
+                        }
+                        float fa[8], fb[8], fc[8];
+                        f2_unpack8(va[u], fa); f2_unpack8(b4, fb); f2_unpack8(c4, fc);
+                        uint32_t q4[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)          // interpolate_gpu.cu:90-99 in its FMUL/FFMA/FFMA order (common.cuh)
-                        o[q] = pack_bf16(interp3(fa[2 * q], w1, fb[2 * q], w2, fc[2 * q], w3),
-                                         interp3(fa[2 * q + 1], w1, fb[2 * q + 1], w2, fc[2 * q + 1], w3));
-                    *reinterpret_cast<uint4 *>(dst + ((ch ^ (r & 7)) << 4)) = valid ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u);
+                        for (int q = 0; q < 4; ++q)      // interpolate_gpu.cu:90-99 in its FMUL/FFMA/FFMA order (common.cuh)
+                            q4[q] = pack_bf16(interp3(fa[2 * q], w1, fb[2 * q], w2, fc[2 * q], w3),
+                                              interp3(fa[2 * q + 1], w1, fb[2 * q + 1], w2, fc[2 * q + 1], w3));
+                        o = valid ? make_uint4(q4[0], q4[1], q4[2], q4[3]) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    *reinterpret_cast<uint4 *>(dst + (size_t)kb * kF2Tile * 128u) = o;
                 }
-            } else {
-                const __nv_bfloat16 *src = sk + (kb - nk) * kF2Slab;
-                uint4 v[8];
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) v[ch] = valid ? __ldg(reinterpret_cast<const uint4 *>(src) + ch) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4 *>(dst + ((ch ^ (r & 7)) << 4)) = v[ch];
             }
         }
     }
     fence_proxy_async();
     __syncthreads();
+    PN2_FP2_MARK()
 
     // ---- layer 1: D1[128][q1] = A[128][k0] W1q[q1][k0]^T ------------------------------------------------------------
     if (warp == 0) {
@@ -276,14 +311,18 @@ fp_tc2_kernel(const Fp2Params p)
     }
     tc_mbar_wait(bar_m1, 0);
     tc_fence_after();
+    PN2_FP2_MARK()
     if (tid == 0) {
         // the A operand is dead in THIS CTA: fetch the W2 quarter into its tail (behind the A1 area the cluster fills)
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w2), "r"(s.w2q_bytes) : "memory");
-        for (int t = 0; t < s.nslab1; ++t)
+        for (int i = 0; i < s.nslab1; ++i) {
+            const int t = (i + tile) % s.nslab1;
             f2_bulk_load(smem_u32(w2q) + (uint32_t)t * s.q2 * 128u,
                          p.image + s.w1_bytes + (size_t)t * s.c2 * 128u + (size_t)rank * s.q2 * 128u, (uint32_t)s.q2 * 128u, bar_w2);
+        }
     }
     f2_cluster_sync();        // every CTA has finished reading ITS A operand: the A1 areas may be overwritten
+    PN2_FP2_MARK()
 
     // ---- epilogue 1: + bias, ReLU, bf16 -> columns [rank*q1, +q1) of the A1 operand of all four CTAs ----------------
     if (warp < 4) {
@@ -310,7 +349,9 @@ fp_tc2_kernel(const Fp2Params p)
         tc_fence_before();
     }
     asm volatile("fence.proxy.async;" ::: "memory");
+    PN2_FP2_MARK()
     f2_cluster_sync();        // all four quarters of A1 have landed everywhere
+    PN2_FP2_MARK()
     fence_proxy_async();
 
     // ---- layer 2: D2[128][q2] = A1[128][c1] W2q[q2][c1]^T -------------------------------------------------------------
@@ -331,6 +372,7 @@ fp_tc2_kernel(const Fp2Params p)
     }
     tc_mbar_wait(bar_m2, 0);
     tc_fence_after();
+    PN2_FP2_MARK()
 
     // ---- epilogue 2: + bias, ReLU -> (B, c2, n) fp32 and the bf16 rows the next layer reads ---------------------------
     if (warp < 4) {
@@ -362,12 +404,20 @@ fp_tc2_kernel(const Fp2Params p)
         tc_fence_before();
     }
     __syncthreads();
+    PN2_FP2_MARK()
+#undef PN2_FP2_MARK
     if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
 }  // namespace pn2
 
 using namespace pn2;
+
+static long long *g_fp2_prof = nullptr;
+// Diagnostic: while prof (device, 16 x int64) is non-NULL, thread 0 of CTA 0 of pn2_fp_tc2_forward records its SM clock
+// at: start, after setup + first cluster barrier, after three_nn, after its exchange, after the A operand, after layer
+// 1, after the "A free" barrier, after epilogue 1, after its barrier, after layer 2, end.
+extern "C" int pn2_debug_fp_tc2_profile(long long *prof) { g_fp2_prof = prof; return PN2_OK; }
 
 extern "C" int pn2_fp_tc2_supported(int c_known, int c_skip, int c1, int c2, int m)
 {
@@ -391,6 +441,7 @@ extern "C" int pn2_fp_tc2_forward(int b, int n, int m, int c_known, int c_skip, 
     p.image = static_cast<const unsigned char *>(weight_image);
     p.out = out;
     p.out_rows = static_cast<__nv_bfloat16 *>(out_rows);
+    p.prof = g_fp2_prof;
     const long long ctas = (long long)b * p.tiles_per_scene * kF2Cluster;
     if (ctas > 0x7fffffffLL) return PN2_ERR_INVALID_ARGUMENT;
     PN2_CUDA_TRY(cudaFuncSetAttribute(fp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.s.smem_bytes));

@@ -421,7 +421,13 @@ def fp_layer(precision, img, unknown, known, known_rows, skip_rows, want_rows=Tr
     B, n, _ = unknown.shape
     m = known.shape[1]
     dims = img.dims
-    if precision == "bf16" and not img.f32_only and len(dims) == 3 and os.environ.get("PN2_FP_TC2", "1") != "0":
+    # The cluster kernel is the low-latency one (config 1: 20 us against 58 us for three_nn + fp_tc at B = 1) but holds four
+    # SMs per 128-point tile; with many tiles in a launch (and batches overlapping on other streams) the single-CTA kernel
+    # costs less SM time per layer (measured at B = 8, 8 batches in flight: 11.5 k against 10.1 k scenes/s).  PN2_FP_TC2
+    # = 1 / 0 forces one or the other.
+    mode = os.environ.get("PN2_FP_TC2", "auto")
+    use_tc2 = mode == "1" or (mode == "auto" and B * ((n + 127) // 128) * 4 <= 64)
+    if precision == "bf16" and not img.f32_only and len(dims) == 3 and use_tc2:
         c_known = known_rows.shape[2]
         c_skip = 0 if skip_rows is None else skip_rows.shape[2]
         if known_rows.dtype == torch.bfloat16 and (skip_rows is None or skip_rows.dtype == torch.bfloat16) and \
