@@ -2,7 +2,8 @@
 (scripts/gpu_profile_r1.sh -> gpurun_out/prof_step_r1.ncu-rep).  Runs in the CPU-only container."""
 import csv, io, json, subprocess, sys
 
-rep = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/prof_step_r1.ncu-rep"
+rep = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/prof_step_r2.ncu-rep"
+out_md = sys.argv[2] if len(sys.argv) > 2 else "profiles/r2_ncu_step.md"
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -37,10 +38,10 @@ for r in data:
                   g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"), g("launch__registers_per_thread"),
                   g("launch__grid_size"), g("launch__block_size"), g("smsp__issue_active.avg.pct_of_peak_sustained_active")))
 json.dump(traffic, open("profiles/ncu_traffic.json", "w"), indent=1, sort_keys=True)
-with open("profiles/r1_ncu_step.md", "w") as f:
+with open(out_md, "w") as f:
     f.write("# One bench step (B=8, 40k points, bf16 arm, lanes=1) under `ncu --set full --clock-control none`\n\n"
             "Per-launch numbers are cold-cache and serialised (compare shares, not absolutes).  `traffic` = DRAM read + write.\n\n"
             "| bench name | kernel | time | DRAM rd MB | DRAM wr MB | DRAM % | tensor % | regs | grid | block | issue % |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
     for t in table:
         f.write("| " + " | ".join(t) + " |\n")
-print(open("profiles/r1_ncu_step.md").read())
+print(open(out_md).read())

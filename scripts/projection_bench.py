@@ -109,6 +109,21 @@ for v in range(V):
     if refs[v] is not None:
         o = ref_project(v, *refs[v])
 torch.cuda.synchronize(); t_ref_pr = (time.perf_counter() - t0) * 1e3
+# across-view max-pooling (the multiview feature of every point): one pass here, against the dense project_views + max
+# of this library and against the reference's per-frame project() folded with a running torch.max
+pooled = helper.project_views_maxpool(label, i3, i2, N)
+t_pool = timed(lambda: helper.project_views_maxpool(label, i3, i2, N), steps=5)
+dense = helper.project_views(label, i3, i2, N)
+pool_same = bool(torch.equal(pooled, torch.clamp_min(dense.max(dim=0)[0], 0.0).t().contiguous()))
+del dense
+torch.cuda.synchronize(); t0 = time.perf_counter()
+acc_ref = label.new_zeros(C, N)
+for v in range(V):
+    if refs[v] is not None:
+        acc_ref = torch.maximum(acc_ref, ref_project(v, *refs[v]))
+torch.cuda.synchronize(); t_ref_pool = (time.perf_counter() - t0) * 1e3
+pool_same_ref = bool(torch.equal(pooled, acc_ref.t().contiguous()))
+b_pool = N * C * 4 + V * (N + 1) * 16 + V * C * dims[0] * dims[1] * 4
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 peak = float(peaks.get("hbm_gbs", 6552.6))
 b_cp = V * (N + 1) * 16 + N * 12 + V * dims[0] * dims[1] * 4
@@ -117,6 +132,9 @@ print(json.dumps({"workload": "projection N=%d views=%d C=%d" % (N, V, C), "corr
                   "compute_projection_ms": round(t_cp, 4), "compute_projection_GBps": round(b_cp / t_cp / 1e6, 1),
                   "compute_projection_frac": round(b_cp / t_cp / 1e6 / peak, 3), "view_points_per_s": round(V * N / t_cp * 1e3),
                   "project_ms": round(t_pr, 4), "project_GBps": round(b_pr / t_pr / 1e6, 1), "project_frac": round(b_pr / t_pr / 1e6 / peak, 3),
+                  "maxpool_ms": round(t_pool, 4), "maxpool_GBps": round(b_pool / t_pool / 1e6, 1),
+                  "maxpool_equals_dense_project_then_max": pool_same, "maxpool_equals_reference_sequence": pool_same_ref,
+                  "reference_sequence_project_and_max_ms": round(t_ref_pool, 2),
                   "hbm_peak_GBps": peak, "reference_sequence_compute_projection_ms": round(t_ref_cp, 2),
                   "reference_sequence_project_ms": round(t_ref_pr, 2),
                   "views_identical_to_reference_sequence": "%d/%d" % (same, checked)}))

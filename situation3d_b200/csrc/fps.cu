@@ -203,6 +203,7 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
 
     uint64_t px2[P / 2], py2[P / 2], pz2[P / 2];
     float pt[P];
+    const bool vec4 = (pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < P; i += 2) {
         float c[2][3], t[2];
@@ -212,9 +213,18 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
             c[h][0] = c[h][1] = c[h][2] = 0.f;
             t[h] = -1.f;                                 // -1: never a candidate (fminf keeps it at -1)
             if (k >= 0) {
-                c[h][0] = __ldg(p + (size_t)pitch * k);
-                c[h][1] = __ldg(p + (size_t)pitch * k + 1);
-                c[h][2] = __ldg(p + (size_t)pitch * k + 2);
+                if (vec4) {
+                    // rows of point_clouds (pitch 132 floats): one 16-byte load per point with a 64-byte L2 fetch hint instead
+                    // of three scalar loads -- each used to pull a whole 128-byte line out of DRAM for 12 useful bytes
+                    float4 v;
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + (size_t)pitch * k));
+                    c[h][0] = v.x; c[h][1] = v.y; c[h][2] = v.z;
+                } else {
+                    c[h][0] = __ldg(p + (size_t)pitch * k);
+                    c[h][1] = __ldg(p + (size_t)pitch * k + 1);
+                    c[h][2] = __ldg(p + (size_t)pitch * k + 2);
+                }
                 if (cp) { cp[3 * (size_t)k] = c[h][0]; cp[3 * (size_t)k + 1] = c[h][1]; cp[3 * (size_t)k + 2] = c[h][2]; }
                 // sampling_gpu.cu:100-101: float mag compared against the double literal 1e-3
                 if (!((double)sqnorm3(c[h][0], c[h][1], c[h][2]) <= 1e-3)) t[h] = 1e10f;   // sampling.cpp:74-76

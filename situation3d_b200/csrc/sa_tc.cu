@@ -34,6 +34,7 @@
 // arithmetic.  sa_tc_v3_kernel (further down) is the software-pipelined one the backbone's shapes run on:
 // several tiles in flight, one warp role per pipeline stage, layer-2 activations kept in TMEM.
 #include "tc_common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace pn2 {
@@ -167,6 +168,7 @@ struct SaTcParams {
     int n, npoint, tiles_per_scene, ntiles;
     int nregion, nslot;     // pipelined kernel: shared-memory tile regions (<= 8) and TMEM accumulator slots (2 or 4)
     uint32_t blk;
+    int use_tma;            // pipelined kernel: neighbour rows fetched by TMA (cp.async.bulk.tensor ... tile::gather4) instead of cp.async
     int debug;              // diagnostics (PN2_SA_TC_DEBUG): 1 skip the feature gather, 4 skip E2's proxy fence, 32 gather rows 0..127
     long long *prof;        // diagnostics: per-phase SM cycles of CTA 0 (16 x int64) or NULL
     float inv_radius;
@@ -565,7 +567,7 @@ __device__ __forceinline__ void v3_epi3(const SaTcParams &p, uint32_t d_taddr, i
 
 template <int NS, int C1, int C2, int C3, int NCHUNK, bool PROF>
 __global__ void __launch_bounds__(kV3Threads, 1)
-sa_tc_v3_kernel(const SaTcParams p)
+sa_tc_v3_kernel(const SaTcParams p, const __grid_constant__ CUtensorMap tmap)
 {
     static_assert(C1 % 64 == 0 && C2 % 64 == 0 && C3 % 128 == 0, "whole swizzle tiles");
     constexpr int kAOff = C1 > C2 ? C1 : C2;                               // TMEM column of the layer-2 A operand
@@ -627,6 +629,7 @@ sa_tc_v3_kernel(const SaTcParams p)
         // shuffle (the row's neighbour index) + address + cp.async, all steps independent of each other.
         constexpr int K0 = ((NCHUNK * 8 + 8 + 15) / 16) * 16;
         constexpr int kRowBytes = NCHUNK * 16;
+        constexpr bool kTmaRows = NCHUNK % 8 == 0;        // rows of whole 128-byte swizzle rows: fetchable by TMA gather4
         // cp.async groups in flight behind the one being issued: a tile is published `lag` iterations after its
         // copies were issued; only as far ahead as there are spare regions (a tile must be published before the
         // gather blocks on a region that tile's successors hold)
@@ -675,6 +678,7 @@ sa_tc_v3_kernel(const SaTcParams p)
         }
         int rg = 0, rg_phase = 1;          // region of tile itt and the parity to wait for on its `empty` barrier
         int pg = 0;                        // region of the tile being published (itt - lag)
+        int lag_tiles_pending = 1;
         const bool fixed_rows = (p.debug & 32) != 0;
         int nb0 = fixed_rows ? myrow : load_idx(0), nb1 = fixed_rows ? myrow : load_idx(1);   // tiles it, it+1
         int nb2 = fixed_rows ? myrow : load_idx(2);                                           // tile it+2
@@ -705,6 +709,41 @@ sa_tc_v3_kernel(const SaTcParams p)
             PN2_MARK(0)
             unsigned char *region = ring + (size_t)rg * s.region_bytes;
             const uint32_t a_base = smem_u32(region);
+            if (kTmaRows && p.use_tma) {
+                // TMA gather: one cp.async.bulk.tensor ... tile::gather4 fetches four neighbour rows (64 bf16 = one
+                // 128-byte swizzle row each) straight into the K-major 128B-swizzled operand; lane j < 8 of the warp
+                // takes rows 4j .. 4j+3 of the warp's 32.  The coordinate chunk and the zero padding are ordinary
+                // stores, made visible to the async proxy before the warp's arrive.expect_tx publishes its share.
+                *reinterpret_cast<uint4 *>(region + x_off) =
+                    make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], l[0]), pack_bf16(l[1], l[2]), pack_bf16(1.f, 1.f));
+#pragma unroll
+                for (int ch = NCHUNK + 1; ch < K0 / 8; ++ch)
+                    *reinterpret_cast<uint4 *>(region + kop_chunk_off(kTile, K0, myrow, ch)) = make_uint4(0u, 0u, 0u, 0u);
+                fence_proxy_async();
+                const int grow = bi * p.n + nb;                                   // row of the (B*N, row_elems) table
+                const int j4 = (lane & 7) * 4;
+                const int r0 = __shfl_sync(0xffffffffu, grow, j4), r1 = __shfl_sync(0xffffffffu, grow, j4 + 1),
+                          r2 = __shfl_sync(0xffffffffu, grow, j4 + 2), r3 = __shfl_sync(0xffffffffu, grow, j4 + 3);
+                const uint32_t fb = bar_full + 8u * rg;
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(32u * (uint32_t)kRowBytes) : "memory");
+                __syncwarp();
+                if (lane < 8 && !(p.debug & 1)) {
+                    const uint32_t dst = a_base + (uint32_t)(pw * 32 + j4) * 128u;
+#pragma unroll
+                    for (int t = 0; t < kRowBytes / 128; ++t)
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+                                     " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                                     ::"r"(dst + (uint32_t)t * (kTile * 128u)), "l"(&tmap), "r"(fb), "r"(t * 64), "r"(r0), "r"(r1),
+                                       "r"(r2), "r"(r3) : "memory");
+                } else if (lane == 8 && (p.debug & 1)) {
+                    // diagnostic "no gather": the expected bytes never arrive, complete them by hand
+                    asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"(32u * (uint32_t)kRowBytes) : "memory");
+                }
+                if (++rg == R) { rg = 0; rg_phase ^= 1; }
+                PN2_MARK(2)
+                continue;
+            }
             const unsigned char *tab = reinterpret_cast<const unsigned char *>(p.table) + (size_t)bi * p.n * kRowBytes;
             if (!(p.debug & 1)) {
 #pragma unroll
@@ -734,11 +773,12 @@ sa_tc_v3_kernel(const SaTcParams p)
             PN2_MARK(2)
           }
         }
-        // drain: the last `lag` tiles
+        // drain: the last `lag` tiles (the TMA path publishes through the barrier's transaction count: nothing pending)
+        if (kTmaRows && p.use_tma) lag_tiles_pending = 0;
         cp_async_wait_all();
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0)
+        if (lane == 0 && lag_tiles_pending)
             for (int it = max(nt - lag, 0); it < nt; ++it) { tc_mbar_arrive(bar_full + 8u * pg); pg = pg + 1 == R ? 0 : pg + 1; }
         if (PROF) { if (profiling) for (int i = 0; i < 3; ++i) p.prof[16 + i] = pc[i]; }
     } else if (warp == kV3WarpA) {
@@ -909,14 +949,32 @@ static int launch_v3(const SaTcParams &q, int grid, uint32_t smem, cudaStream_t 
 {
     // the phase profile is compiled for the bench shapes only
     constexpr bool kHasProf = (NS == 64 && C3 == 128) || (NS == 32 && C3 == 256) || (NS == 16 && NCHUNK == 16);
+    // TMA gather of the neighbour rows when a row is a whole number of 128-byte swizzle rows (the per-point layer-1 rows of
+    // csrc/lin_tc.cu: 64 or 128 channels).  The tensor map describes the (B*N, row_elems) table with a one-row box of 64
+    // columns; PN2_SA_TC_TMA=0 keeps the cp.async gather.
+    SaTcParams qq = q;
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    static const bool tma_on = [] { const char *e = getenv("PN2_SA_TC_TMA"); return !e || atoi(e) != 0; }();
+    qq.use_tma = 0;
+    if (NCHUNK % 8 == 0 && tma_on && (reinterpret_cast<uintptr_t>(q.table) & 15) == 0) {
+        const long long rows = (long long)(q.ntiles / q.tiles_per_scene) * q.n;
+        cuuint64_t gdim[2] = {(cuuint64_t)NCHUNK * 8, (cuuint64_t)rows}, gstr[1] = {(cuuint64_t)NCHUNK * 16};
+        cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};
+        if (rows > 0 && rows < (1ll << 31) &&
+            cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(q.table), gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            qq.use_tma = 1;
+    }
     if (kHasProf && q.prof) {
         auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, NCHUNK, kHasProf>;
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kV3Threads, smem, stream>>>(q);
+        kern<<<grid, kV3Threads, smem, stream>>>(qq, tmap);
     } else {
         auto kern = sa_tc_v3_kernel<NS, C1, C2, C3, NCHUNK, false>;
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kV3Threads, smem, stream>>>(q);
+        kern<<<grid, kV3Threads, smem, stream>>>(qq, tmap);
     }
     PN2_LAUNCH_CHECK("sa_tc_forward(pipelined)");
     return PN2_OK;
@@ -1115,7 +1173,7 @@ extern "C" int pn2_sa_tc_forward(int b, int n, int npoint, int nsample, int c, i
     p.image = static_cast<const unsigned char *>(weight_image);
     p.out = out;
     p.out_table = static_cast<__nv_bfloat16 *>(out_table);
-    p.nregion = 0; p.nslot = 0; p.blk = 0;
+    p.nregion = 0; p.nslot = 0; p.blk = 0; p.use_tma = 0;
     { const char *ed = getenv("PN2_SA_TC_DEBUG"); p.debug = ed ? atoi(ed) : 0; }
     p.prof = g_sa_tc_prof;
     switch (nsample) {
