@@ -157,7 +157,9 @@ reencode_v2_kernel(int b, int t, int h, int mode, const float *__restrict__ toke
     float *w2t = re2_smem;                       // [h][D]
     float *hid = w2t + (size_t)h * D;            // [h][kTok2]
     float *pxy = hid + (size_t)h * kTok2;        // [kTok2][2]
+    float *w1s = pxy + 2 * kTok2;                // [h][2] then b1 [h]: the hidden layer's parameters, staged once
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 3 * h; i += kReThreads) w1s[i] = i < 2 * h ? __ldg(w1 + i) : __ldg(b1 + (i - 2 * h));
     // W2 (D, h) row-major -> W2T[h][D].  A warp takes 32 consecutive outputs dd and one 16-byte piece of their rows:
     // the shared-memory stores are conflict-free (consecutive dd), the global reads use half of every 32-byte sector
     // (out of L2, once per CTA); eight independent loads are in flight per thread.
@@ -225,7 +227,7 @@ reencode_v2_kernel(int b, int t, int h, int mode, const float *__restrict__ toke
         // hidden layer: Linear(2, h) + exact GELU (sqa_module.py:274-276), stored [h][token]
         for (int e = tid; e < h * kTok2; e += kReThreads) {
             const int i = e % kTok2, jj = e / kTok2;
-            hid[e] = gelu_erf(fmaf(pxy[2 * i + 1], __ldg(w1 + 2 * jj + 1), fmaf(pxy[2 * i], __ldg(w1 + 2 * jj), __ldg(b1 + jj))));
+            hid[e] = gelu_erf(fmaf(pxy[2 * i + 1], w1s[2 * jj + 1], fmaf(pxy[2 * i], w1s[2 * jj], w1s[2 * h + jj])));
         }
         __syncthreads();
         // product: warp -> tokens 8*warp .. 8*warp+7, lane -> outputs 4*lane..+3 and 128 + 4*lane..+3
@@ -346,7 +348,7 @@ extern "C" int pn2_reencode_forward(int b, int t, int d, int h, int mode, float 
     if (b < 0 || t < 0 || d < 1 || h < 1 || (mode != 0 && mode != 1)) return PN2_ERR_INVALID_ARGUMENT;
     if (b == 0 || t == 0) return PN2_OK;
     if (!tokens || !positions || !situation || !w1 || !b1 || !w2 || !b2 || !out) return PN2_ERR_INVALID_ARGUMENT;
-    const size_t smem2 = sizeof(float) * ((size_t)h * 256 + (size_t)h * kTok2 + 2 * kTok2);
+    const size_t smem2 = sizeof(float) * ((size_t)h * 256 + (size_t)h * kTok2 + 2 * kTok2 + 3 * (size_t)h);
     const bool aligned = ((reinterpret_cast<uintptr_t>(tokens) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(b2)) & 15) == 0;
     if (d == 256 && smem2 <= 200 * 1024 && aligned) {
         // the reference's shape (Linear(128, 256)): W2 resident per CTA, persistent over 64-token tiles
