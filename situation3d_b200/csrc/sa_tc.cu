@@ -961,8 +961,20 @@ static int launch_v3(const SaTcParams &q, int grid, uint32_t smem, cudaStream_t 
         const long long rows = (long long)(q.ntiles / q.tiles_per_scene) * q.n;
         cuuint64_t gdim[2] = {(cuuint64_t)NCHUNK * 8, (cuuint64_t)rows}, gstr[1] = {(cuuint64_t)NCHUNK * 16};
         cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};
-        if (rows > 0 && rows < (1ll << 31) &&
-            cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(q.table), gdim, gstr, box, estr,
+        // the driver entry point is resolved at run time: the library must load on machines without libcuda.so.1
+        typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                          const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static const EncodeTiledFn encode = [] {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult st;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess ||
+                st != cudaDriverEntryPointSuccess)
+                fn = nullptr;
+            return reinterpret_cast<EncodeTiledFn>(fn);
+        }();
+        if (encode && rows > 0 && rows < (1ll << 31) &&
+            encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(q.table), gdim, gstr, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
             qq.use_tma = 1;
