@@ -111,6 +111,17 @@ int pn2_ball_query_ws(int b, int n, int m, float radius, int nsample, const floa
                       const float *xyz, int *idx, void *workspace, size_t workspace_bytes,
                       pn2_stream_t stream);
 
+/* The two halves of pn2_ball_query_ws.  The grid depends on the points and the radius only, so a caller
+ * whose centres come from a sampling kernel on another stream (the backbone's SA1: lib/pointnet2/
+ * pointnet2_modules.py:181-205 runs FPS, then QueryAndGroup) builds it while that kernel runs.
+ * xyz_pitch = floats between consecutive points (3 for (b,n,3), 3+C for point_clouds rows).
+ * Both return PN2_ERR_WORKSPACE when the shape takes the plain scan (workspace_bytes() == 0) or the
+ * workspace is missing/short; the same workspace, untouched in between, must be passed to both. */
+int pn2_ball_query_grid_build(int b, int n, int m, float radius, int nsample, const float *xyz,
+                              int xyz_pitch, void *workspace, size_t workspace_bytes, pn2_stream_t stream);
+int pn2_ball_query_grid_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                              int *idx, void *workspace, size_t workspace_bytes, pn2_stream_t stream);
+
 /* points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample) */
 int pn2_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
                      const int *idx, float *out, pn2_stream_t stream);

@@ -135,9 +135,16 @@ class Pointnet2Backbone(nn.Module):
             src_xyz, table, ld, c, skip = xyz, pc[..., 3:], W, W - 3, 3
         else:
             src_xyz, table, ld, c, skip = xyz, rows_bf16, rows_bf16.shape[2], self.input_feature_dim, 3
+        # SA1's ball-query grid needs the scene only, not the centres: built here, it runs under the first
+        # sampling kernel instead of after it
+        grid0 = _fused.ball_query_grid_build(pc if pc is not None else xyz, N, sas[0].npoint, sas[0].radius,
+                                             sas[0].nsample)
         for lvl, m in enumerate(sas):
             main.wait_event(ready[lvl])
-            idx = _fused.ball_query(src_xyz, cxyz[lvl], m.radius, m.nsample)
+            if lvl == 0 and grid0 is not None:
+                idx = _fused.ball_query_grid_query(grid0, N, cxyz[0], m.radius, m.nsample)
+            else:
+                idx = _fused.ball_query(src_xyz, cxyz[lvl], m.radius, m.nsample)
             inv_r = 1.0 / m.radius if m.normalize_xyz else 1.0
             out, out_rows = _fused.SA_FORWARD[self.precision](imgs[lvl], src_xyz, cxyz[lvl], idx, table, ld, c,
                                                              m.use_xyz, inv_r, raw_skip=skip)

@@ -173,7 +173,7 @@ __device__ __forceinline__ void take_later_if_greater(Cand &a, const Cand &b)
 // P = point slots per thread (even).  REGS: xyz of the slots are kept in registers (P <= 16); otherwise
 // they are read back from this CTA's shared-memory copy each round.  CLUSTER: compiled-in switch
 // between the single-CTA exchange (shared memory + bar.sync) and the DSMEM exchange.
-template <int P, bool REGS, bool CLUSTER, int MAXT, int MINB>
+template <int P, bool REGS, bool CLUSTER, int MAXT, int MINB, int RP = (REGS ? P / 2 : 0)>
 __global__ void __launch_bounds__(MAXT, MINB)
 fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int pitch, int *__restrict__ idxs,
            float *__restrict__ new_xyz, float *__restrict__ xyz_copy, long long *__restrict__ prof)
@@ -201,7 +201,11 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
     const int myslot = (int)rank * W + warp;
     const uint32_t mypos = (uint32_t)((myslot % K) * 32 + myslot / K);
 
-    uint64_t px2[P / 2], py2[P / 2], pz2[P / 2];
+    // slot (i, tid) of the shared-memory copy: the two slots of a pair are adjacent (one 8-byte access per pair)
+    auto sidx = [&](int i) { return ((i >> 1) * T + tid) * 2 + (i & 1); };
+    // RP = slot pairs whose coordinates stay in registers; the others are re-read from shared memory each round
+    // (fewer registers per thread -> more scenes resident per SM)
+    uint64_t px2[RP > 0 ? RP : 1], py2[RP > 0 ? RP : 1], pz2[RP > 0 ? RP : 1];
     float pt[P];
     const bool vec4 = (pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 #pragma unroll
@@ -229,9 +233,11 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
                 // sampling_gpu.cu:100-101: float mag compared against the double literal 1e-3
                 if (!((double)sqnorm3(c[h][0], c[h][1], c[h][2]) <= 1e-3)) t[h] = 1e10f;   // sampling.cpp:74-76
             }
-            sx[(i + h) * T + tid] = c[h][0]; sy[(i + h) * T + tid] = c[h][1]; sz[(i + h) * T + tid] = c[h][2];
+            sx[sidx(i + h)] = c[h][0]; sy[sidx(i + h)] = c[h][1]; sz[sidx(i + h)] = c[h][2];
         }
-        px2[i / 2] = pack2(c[0][0], c[1][0]); py2[i / 2] = pack2(c[0][1], c[1][1]); pz2[i / 2] = pack2(c[0][2], c[1][2]);
+        if (i / 2 < RP) {
+            px2[i / 2] = pack2(c[0][0], c[1][0]); py2[i / 2] = pack2(c[0][1], c[1][1]); pz2[i / 2] = pack2(c[0][2], c[1][2]);
+        }
         pt[i] = t[0]; pt[i + 1] = t[1];
     }
     for (int i = tid; i < 2 * kMaxCluster * kMaxWarps; i += T) (&table[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -285,7 +291,7 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
 #pragma unroll
             for (int i = 0; i + st < P; i += 2 * st) take_later_if_greater(cd[i], cd[i + st]);
         best = cd[0];
-        bx = sx[best.i * T + tid]; by = sy[best.i * T + tid]; bz = sz[best.i * T + tid];
+        bx = sx[sidx(best.i)]; by = sy[sidx(best.i)]; bz = sz[sidx(best.i)];
     };
     tournament();
 
@@ -300,11 +306,13 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
         const bool stale = !kLazy || fminf(sqdist3(bx, by, bz, ox, oy, oz), best.v) != best.v;
 #pragma unroll
         for (int i = 0; i < P; i += 2) {
-            uint64_t x2 = px2[i / 2], y2 = py2[i / 2], z2 = pz2[i / 2];
-            if (!REGS) {
-                x2 = pack2(sx[i * T + tid], sx[(i + 1) * T + tid]);
-                y2 = pack2(sy[i * T + tid], sy[(i + 1) * T + tid]);
-                z2 = pack2(sz[i * T + tid], sz[(i + 1) * T + tid]);
+            uint64_t x2, y2, z2;
+            if (i / 2 < RP) {
+                x2 = px2[i / 2]; y2 = py2[i / 2]; z2 = pz2[i / 2];
+            } else {
+                x2 = *reinterpret_cast<const uint64_t *>(sx + sidx(i));
+                y2 = *reinterpret_cast<const uint64_t *>(sy + sidx(i));
+                z2 = *reinterpret_cast<const uint64_t *>(sz + sidx(i));
             }
             // (x - ox)^2 + (y - oy)^2 + (z - oz)^2 as FMUL, FFMA, FFMA with the x term first (sqdist3)
             const uint64_t dx = add2(x2, nx2), dy = add2(y2, ny2), dz = add2(z2, nz2);
@@ -474,7 +482,14 @@ static int dispatch(const FpsPlan &pl, int b, int n, int m, const float *xyz, in
 #define PN2_FPS_CASE(P, REGS, MAXT) \
     case P: return launch<P, REGS, MAXT>(pl, b, n, m, xyz, pitch, idxs, new_xyz, xyz_copy, prof, s)
     if (pl.threads == 128 && pl.ppt == 40 && pl.cluster > 1) {
-        auto kern = fps_kernel<40, true, true, 128, 2>;
+        // PN2_FPS_RP (tuning): slot pairs kept in registers; fewer -> three CTAs per SM instead of two
+        static const int rp = [] { const char *e = getenv("PN2_FPS_RP"); return e ? atoi(e) : 20; }();
+        auto kern = rp == 0 ? fps_kernel<40, false, true, 128, 3, 0>
+                  : rp == 4 ? fps_kernel<40, false, true, 128, 3, 4>
+                  : rp == 6 ? fps_kernel<40, false, true, 128, 3, 6>
+                  : rp == 8 ? fps_kernel<40, false, true, 128, 3, 8>
+                  : rp == 10 ? fps_kernel<40, false, true, 128, 3, 10>
+                            : fps_kernel<40, true, true, 128, 2>;
         const size_t smem = (size_t)3 * 40 * 128 * sizeof(float);
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};

@@ -131,16 +131,17 @@ __device__ __forceinline__ int grid_axis_cell(float v, float mn, float inv, int 
 }
 
 __global__ void __launch_bounds__(1024)
-bq_grid_setup_kernel(int n, float cell_min, const float *__restrict__ xyz, GridParams *__restrict__ params)
+bq_grid_setup_kernel(int n, int pitch, float cell_min, const float *__restrict__ xyz,
+                     GridParams *__restrict__ params)
 {
     __shared__ float red[6][32];
     const size_t bi = blockIdx.x;
-    const float *p = xyz + bi * (size_t)n * 3;
+    const float *p = xyz + bi * (size_t)n * pitch;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for (int k = threadIdx.x; k < n; k += blockDim.x)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float v = __ldg(p + 3 * (size_t)k + a);
+            const float v = __ldg(p + (size_t)pitch * k + a);
             if (isfinite(v)) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
         }
 #pragma unroll
@@ -187,14 +188,14 @@ __device__ __forceinline__ int grid_point_cell(const GridParams &g, float x, flo
 
 // pass 0: count points per cell; pass 1: scatter (x, y, z, index) into cell order
 __global__ void __launch_bounds__(256)
-bq_grid_bin_kernel(int n, int pass, const float *__restrict__ xyz, const GridParams *__restrict__ params,
-                   int *__restrict__ cursor, float4 *__restrict__ sorted)
+bq_grid_bin_kernel(int n, int pitch, int pass, const float *__restrict__ xyz,
+                   const GridParams *__restrict__ params, int *__restrict__ cursor, float4 *__restrict__ sorted)
 {
     const size_t bi = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const GridParams g = params[bi];
-    const float *p = xyz + (bi * n + k) * 3;
+    const float *p = xyz + (bi * n + k) * (size_t)pitch;
     const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
     const int cell = grid_point_cell(g, x, y, z);
     if (cell < 0) return;
@@ -392,38 +393,84 @@ extern "C" size_t pn2_ball_query_workspace_bytes(int b, int n, int m, int nsampl
     return (size_t)b * (sizeof(GridParams) + 2 * sizeof(int) * (size_t)(kGridMaxCells + 1) + sizeof(float4) * (size_t)n) + 256;
 }
 
+namespace {
+
+struct GridWs {
+    GridParams *params;
+    float4 *sorted;
+    int *cursor, *start;
+    int wpl, warps;
+    size_t per_warp;
+};
+
+// Carves the workspace; false when this shape takes the plain scan (small scene, no/short workspace, a ball
+// that cannot be realised as a grid).
+bool grid_ws(int b, int n, int m, float radius, int nsample, void *workspace, size_t workspace_bytes, GridWs &g)
+{
+    const size_t need = pn2_ball_query_workspace_bytes(b, n, m, nsample);
+    g.wpl = (ceil_div(n, 1024)) | 1;                             // bitmap words per lane, odd: conflict-free slices
+    g.per_warp = sizeof(int) * ((size_t)g.wpl * 32 + nsample);
+    g.warps = (int)min((size_t)kGqWarps, (size_t)(200 * 1024) / max(g.per_warp, (size_t)1));
+    if (need == 0 || !workspace || workspace_bytes < need || g.warps < 1 || !(radius > 0.f) || m <= 0 || nsample <= 0)
+        return false;
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    w += (256 - (reinterpret_cast<uintptr_t>(w) & 255)) & 255;
+    g.params = reinterpret_cast<GridParams *>(w);
+    g.sorted = reinterpret_cast<float4 *>(w + (((size_t)b * sizeof(GridParams) + 15) & ~(size_t)15));
+    g.cursor = reinterpret_cast<int *>(g.sorted + (size_t)b * n);
+    g.start = g.cursor + (size_t)b * (kGridMaxCells + 1);
+    return true;
+}
+
+}   // namespace
+
+// The grid depends on the points and the radius only, not on the centres: a caller whose centres come from a
+// sampling kernel on another stream builds the grid while that kernel runs and queries it afterwards.
+extern "C" int pn2_ball_query_grid_build(int b, int n, int m, float radius, int nsample, const float *xyz,
+                                         int xyz_pitch, void *workspace, size_t workspace_bytes,
+                                         pn2_stream_t stream)
+{
+    GridWs g;
+    if (b <= 0 || n <= 0 || b > 65535 || !xyz || xyz_pitch < 3) return PN2_ERR_INVALID_ARGUMENT;
+    if (!grid_ws(b, n, m, radius, nsample, workspace, workspace_bytes, g)) return PN2_ERR_WORKSPACE;
+    cudaStream_t s = as_stream(stream);
+    PN2_CUDA_TRY(cudaMemsetAsync(g.cursor, 0, sizeof(int) * (size_t)b * (kGridMaxCells + 1), s));
+    bq_grid_setup_kernel<<<b, 1024, 0, s>>>(n, xyz_pitch, radius * 1.001f, xyz, g.params);
+    dim3 pgrid(ceil_div(n, 256), b);
+    bq_grid_bin_kernel<<<pgrid, 256, 0, s>>>(n, xyz_pitch, 0, xyz, g.params, g.cursor, g.sorted);
+    bq_grid_scan_kernel<<<b, 1024, 0, s>>>(g.params, g.cursor, g.start);
+    bq_grid_bin_kernel<<<pgrid, 256, 0, s>>>(n, xyz_pitch, 1, xyz, g.params, g.cursor, g.sorted);
+    count_launches(3);   // setup, bin x2, scan (one is counted by the check below)
+    PN2_LAUNCH_CHECK("ball_query_grid_build");
+    return PN2_OK;
+}
+
+extern "C" int pn2_ball_query_grid_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                                         int *idx, void *workspace, size_t workspace_bytes, pn2_stream_t stream)
+{
+    GridWs g;
+    if (b <= 0 || n <= 0 || b > 65535 || !new_xyz || !idx) return PN2_ERR_INVALID_ARGUMENT;
+    if (!grid_ws(b, n, m, radius, nsample, workspace, workspace_bytes, g)) return PN2_ERR_WORKSPACE;
+    PN2_CUDA_TRY(cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    dim3 qgrid(ceil_div(m, g.warps), b);
+    bq_grid_query_kernel<<<qgrid, g.warps * 32, g.per_warp * g.warps, as_stream(stream)>>>(
+        n, m, radius * radius, nsample, g.wpl, g.warps, new_xyz, g.params, g.start, g.sorted, idx);
+    PN2_LAUNCH_CHECK("ball_query_grid");
+    return PN2_OK;
+}
+
 extern "C" int pn2_ball_query_ws(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                                  const float *xyz, int *idx, void *workspace, size_t workspace_bytes,
                                  pn2_stream_t stream)
 {
-    const size_t need = pn2_ball_query_workspace_bytes(b, n, m, nsample);
-    const int wpl = (ceil_div(n, 1024)) | 1;                     // bitmap words per lane, odd: conflict-free slices
-    const size_t per_warp = sizeof(int) * ((size_t)wpl * 32 + nsample);
-    const int warps = (int)min((size_t)kGqWarps, (size_t)(200 * 1024) / max(per_warp, (size_t)1));
+    GridWs g;
     // small scenes, balls that cannot be realised as a grid, or no workspace: the plain scan
-    if (need == 0 || !workspace || workspace_bytes < need || warps < 1 || !(radius > 0.f) || m <= 0 || nsample <= 0)
+    if (!grid_ws(b, n, m, radius, nsample, workspace, workspace_bytes, g))
         return pn2_ball_query(b, n, m, radius, nsample, new_xyz, xyz, idx, stream);
     if (b > 65535 || !new_xyz || !xyz || !idx) return PN2_ERR_INVALID_ARGUMENT;
-    cudaStream_t s = as_stream(stream);
-    unsigned char *w = static_cast<unsigned char *>(workspace);
-    w += (256 - (reinterpret_cast<uintptr_t>(w) & 255)) & 255;
-    GridParams *params = reinterpret_cast<GridParams *>(w);
-    float4 *sorted = reinterpret_cast<float4 *>(w + (((size_t)b * sizeof(GridParams) + 15) & ~(size_t)15));
-    int *cursor = reinterpret_cast<int *>(sorted + (size_t)b * n);
-    int *start = cursor + (size_t)b * (kGridMaxCells + 1);
-    PN2_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)b * (kGridMaxCells + 1), s));
-    bq_grid_setup_kernel<<<b, 1024, 0, s>>>(n, radius * 1.001f, xyz, params);
-    dim3 pgrid(ceil_div(n, 256), b);
-    bq_grid_bin_kernel<<<pgrid, 256, 0, s>>>(n, 0, xyz, params, cursor, sorted);
-    bq_grid_scan_kernel<<<b, 1024, 0, s>>>(params, cursor, start);
-    bq_grid_bin_kernel<<<pgrid, 256, 0, s>>>(n, 1, xyz, params, cursor, sorted);
-    PN2_CUDA_TRY(cudaFuncSetAttribute(bq_grid_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    dim3 qgrid(ceil_div(m, warps), b);
-    bq_grid_query_kernel<<<qgrid, warps * 32, per_warp * warps, s>>>(n, m, radius * radius, nsample, wpl, warps, new_xyz,
-                                                                    params, start, sorted, idx);
-    count_launches(4);   // setup, bin x2, scan (the query kernel is counted by the check below)
-    PN2_LAUNCH_CHECK("ball_query_grid");
-    return PN2_OK;
+    const int rc = pn2_ball_query_grid_build(b, n, m, radius, nsample, xyz, 3, workspace, workspace_bytes, stream);
+    if (rc != PN2_OK) return rc;
+    return pn2_ball_query_grid_query(b, n, m, radius, nsample, new_xyz, idx, workspace, workspace_bytes, stream);
 }
 
 extern "C" int pn2_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,

@@ -248,6 +248,30 @@ def ball_query(xyz, new_xyz, radius, nsample, out=None):
     return idx
 
 
+def ball_query_grid_build(points, n, m, radius, nsample):
+    """Builds the uniform grid over `points` ((B, n, pitch) f32, xyz in the first three columns) on the
+    current stream; returns the workspace for ball_query_grid_query, or None when this shape takes the
+    plain scan.  The grid needs no centres, so it can be built while the sampling kernel still runs."""
+    B, pitch = points.shape[0], points.shape[2]
+    nbytes = lib.pn2_ball_query_workspace_bytes(B, n, m, int(nsample))
+    if not nbytes or not radius > 0:
+        return None
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
+    with torch.cuda.device(points.device):
+        check(lib.pn2_ball_query_grid_build(B, n, m, float(radius), int(nsample), ptr(points), pitch, ptr(ws),
+                                            nbytes, stream_ptr()), "ball_query_grid_build")
+    return ws
+
+
+def ball_query_grid_query(ws, n, new_xyz, radius, nsample):
+    B, m, _ = new_xyz.shape
+    idx = torch.empty((B, m, nsample), dtype=torch.int32, device=new_xyz.device)
+    with torch.cuda.device(new_xyz.device):
+        check(lib.pn2_ball_query_grid_query(B, n, m, float(radius), int(nsample), ptr(new_xyz), ptr(idx), ptr(ws),
+                                            ws.numel(), stream_ptr()), "ball_query_grid_query")
+    return idx
+
+
 def three_nn(unknown, known):
     B, n, _ = unknown.shape
     m = known.shape[1]

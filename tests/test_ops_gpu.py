@@ -186,6 +186,23 @@ def test_ball_query_grid_degenerate_geometry(ext):
         assert torch.equal(got, orc.ball_query(c, x, r, 16))
 
 
+def test_ball_query_grid_built_ahead_from_pitched_rows(ext):
+    """The two halves of the grid path (build from point_clouds rows on one stream, query once the centres
+    exist) give the ascending-scan result; small scenes report that they take the plain scan."""
+    from situation3d_b200 import fused
+    x = cloud(901, 2, 6000, dup=500, zeros=5)
+    rows = torch.cat([x, torch.randn(2, 6000, 5)], dim=2).contiguous().cuda()      # pitch 8
+    c = torch.cat([x[:, :100], cloud(902, 2, 60, scale=3.0)], dim=1).contiguous()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ws = fused.ball_query_grid_build(rows, 6000, c.shape[1], 0.3, 16)
+    assert ws is not None
+    torch.cuda.current_stream().wait_stream(side)
+    got = fused.ball_query_grid_query(ws, 6000, c.cuda(), 0.3, 16).cpu()
+    assert torch.equal(got, orc.ball_query(c, x, 0.3, 16))
+    assert fused.ball_query_grid_build(rows[:, :1000].contiguous(), 1000, 10, 0.3, 16) is None
+
+
 def test_ball_query_full_scene(ext):
     x = scene_xyz([2])
     inds = orc.furthest_point_sampling(x, 2048)
