@@ -540,10 +540,11 @@ class Runner:
         """K timed steps, `lanes` batches in flight, inputs resident in HBM.  Returns (seconds, launches, host ms/step)."""
         import torch
         from situation3d_b200._lib import lib as _pn2
+        from situation3d_b200.streams import lane_stream
         args, dev, model = self.args, self.dev, self.model
         base = torch.cuda.current_stream(dev)
         nl = max(1, self.cfg["lanes"])
-        self.lanes = [part.stream(part.MAIN) if part else torch.cuda.Stream(device=dev) for _ in range(nl)]
+        self.lanes = [part.stream(part.MAIN) if part else lane_stream(dev) for _ in range(nl)]
         lanes = self.lanes
         outs = [None] * nl
         with torch.no_grad():

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from . import fused as _fused
 from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+from .streams import sampling_stream
 
 
 class Pointnet2Backbone(nn.Module):
@@ -112,7 +113,7 @@ class Pointnet2Backbone(nn.Module):
         side = self._side_streams.get(key)
         if side is None:
             part = self.sm_partition
-            side = part.stream(part.FPS) if part is not None else torch.cuda.Stream(device=dev)
+            side = part.stream(part.FPS) if part is not None else sampling_stream(dev)
             self._side_streams[key] = side
 
         # buffers are allocated on the main stream; the side stream only fills them

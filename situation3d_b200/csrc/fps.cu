@@ -482,13 +482,13 @@ static int dispatch(const FpsPlan &pl, int b, int n, int m, const float *xyz, in
 #define PN2_FPS_CASE(P, REGS, MAXT) \
     case P: return launch<P, REGS, MAXT>(pl, b, n, m, xyz, pitch, idxs, new_xyz, xyz_copy, prof, s)
     if (pl.threads == 128 && pl.ppt == 40 && pl.cluster > 1) {
-        // PN2_FPS_RP (tuning): slot pairs kept in registers; fewer -> three CTAs per SM instead of two
+        // PN2_FPS_RP (tuning): slot pairs whose coordinates stay in registers.  6 or 0 -> 168 registers, three CTAs
+        // per SM instead of two.  Measured (scripts/fps_rp_sweep.py, fps_sat_one.py): 48 scenes resident instead of
+        // 32, but +33 % instructions per round (LDS + moves) and a slower round (1.54 vs 1.35 ms alone), so the
+        // saturated throughput is the same within 4 % (0.393 vs 0.408 ms per 8 scenes) -- default stays all-register.
         static const int rp = [] { const char *e = getenv("PN2_FPS_RP"); return e ? atoi(e) : 20; }();
         auto kern = rp == 0 ? fps_kernel<40, false, true, 128, 3, 0>
-                  : rp == 4 ? fps_kernel<40, false, true, 128, 3, 4>
                   : rp == 6 ? fps_kernel<40, false, true, 128, 3, 6>
-                  : rp == 8 ? fps_kernel<40, false, true, 128, 3, 8>
-                  : rp == 10 ? fps_kernel<40, false, true, 128, 3, 10>
                             : fps_kernel<40, true, true, 128, 2>;
         const size_t smem = (size_t)3 * 40 * 128 * sizeof(float);
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

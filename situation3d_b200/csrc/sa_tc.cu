@@ -1074,7 +1074,18 @@ static int launch_sa_tc(const SaTcParams &p_in, cudaStream_t stream)
             if (const char *er = getenv("PN2_SA_TC_V2_REGIONS")) q.nregion = max(T, min(R, atoi(er)));
             const uint32_t smem2 = 1024u + p.s.w1_bytes + p.s.w2_bytes + p.s.w3_bytes + p.s.bias_bytes + 8u * kV3Bars + 16u +
                                    (uint32_t)q.nregion * p.s.region_bytes;
-            const int grid = min(p.ntiles, sms);
+            // Grid: one persistent CTA per SM, but never fewer than `min_tiles` tiles per CTA once the launch would
+            // fill the GPU anyway.  A CTA's prologue (weight image, TMEM, barriers: ~8 us) costs as much as 2-3 tiles;
+            // at SA3/SA4 (512 / 256 tiles per 8-scene batch) 148 CTAs spend most of their SM time in it, and a step
+            // with several batches in flight is bound by SM time, not by this kernel's latency.  Tiles are spread
+            // evenly (ceil), so the duration is prologue + per tiles.  PN2_SA_TC_MIN_TILES=1: one CTA per SM always.
+            static const int min_tiles = [] { const char *e = getenv("PN2_SA_TC_MIN_TILES"); return e ? max(1, atoi(e)) : 8; }();
+            int grid = min(p.ntiles, sms);
+            if (p.ntiles > sms) {
+                const int g0 = min(sms, max(1, p.ntiles / min_tiles));
+                const int per = (p.ntiles + g0 - 1) / g0;
+                grid = (p.ntiles + per - 1) / per;
+            }
             return dispatch_v3<NS>(q, grid, smem2, stream);
         }
     }

@@ -15,6 +15,8 @@ images of the fused layers: capture again after the module's parameters change.
 """
 import torch
 
+from .streams import lane_stream
+
 
 def _as_inputs(example):
     """A (B,N,3+C) f32 tensor -> {"point_clouds": t}; an (xyz f32, feature rows bf16) pair -- the compact transport
@@ -32,7 +34,7 @@ class GraphedBackbone:
         self.net = net
         example = _as_inputs(example)
         first = next(iter(example.values()))
-        self.stream = stream if stream is not None else torch.cuda.Stream(device=first.device)
+        self.stream = stream if stream is not None else lane_stream(first.device)
         self.static_in = _as_inputs(static_input) if static_input is not None else {k: torch.empty_like(v) for k, v in example.items()}
         from ._lib import lib
         with torch.no_grad():
@@ -83,7 +85,7 @@ class BackbonePipeline:
         first = next(iter(example.values()))
         dev = first.device if first.is_cuda else torch.device("cuda", torch.cuda.current_device())
         example = {k: v.to(dev) for k, v in example.items()}
-        self.streams = list(streams) if streams is not None else [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        self.streams = list(streams) if streams is not None else [lane_stream(dev) for _ in range(lanes)]
         self.inputs = [{k: v.clone() for k, v in example.items()} for _ in self.streams]
         self.steps = [GraphedBackbone(net, example, stream=st, static_input=buf) for st, buf in zip(self.streams, self.inputs)]
         self.outputs = tuple(outputs)
