@@ -414,8 +414,50 @@ int pn2_rotation_vectors_to_matrices(int b, const float *rotvecs, float *out, pn
 int pn2_situation_matrices(int b, const float *situation, float *out, pn2_stream_t stream);
 
 #if defined(__GNUC__)
-#pragma GCC visibility pop
 #endif
+/* ---- training-mode BatchNorm + ReLU (+ max-pool over nsample) on channel-last rows -------------------------------
+ * Replaces, for the training step (BASELINE.json config 4), the element-wise chain the reference runs per SharedMLP
+ * layer -- BatchNorm2d (batch statistics, biased variance, eps inside the root) -> ReLU, lib/pointnet2/pytorch_utils.py:
+ * 11-36,67-121 -- and the F.max_pool2d over nsample that follows the last layer (lib/pointnet2/pointnet2_modules.py:
+ * 259-262), forward and backward.  x, y, dy, dx: (rows, c) fp32 row-major, c % 4 == 0 and 256 % (c/4) == 0
+ * (pn2_rows_bn_supported); a, b, k1, k2, k3: (c,) fp32.
+ *   stats:            partials[cta] = [sum x | sum x^2] over the CTA's rows (no atomics: deterministic); *nparts slots
+ *   finalize:         mean / biased variance -> a = gamma/sqrt(var+eps), b = beta - mean*a, stat = [mean | 1/sqrt(var+eps)]
+ *                     (fp64, for the backward pass); running_mean / running_var (may be NULL) updated as nn.BatchNorm2d
+ *                     does (momentum, unbiased variance)
+ *   apply:            y = max(x*a + b, 0)
+ *   pool:             pooled[g] = max_j y[g*nsample + j], arg[g] = first j attaining it (u8); y itself is not written
+ *   bwd_reduce:       partials[cta] = [sum g | sum g*x],  g = dy where x*a + b > 0 else 0
+ *   bwd_finalize:     dgamma, dbeta and k1..k3 of dx = k1*g + k2 + k3*x (BatchNorm's input gradient)
+ *   bwd_apply:        dx = k1*g + k2 + k3*x
+ *   pool_bwd_*:       the same with g non-zero only at row arg[g] of each group, read from dpooled (groups, c)
+ * partials: pn2_rows_bn_partials_bytes(rows, c) bytes of device memory.                                              */
+int pn2_rows_bn_supported(long long rows, int c, int nsample);
+size_t pn2_rows_bn_partials_bytes(long long rows, int c);
+int pn2_rows_bn_stats(long long rows, int c, const float *x, double *partials, int *nparts, pn2_stream_t stream);
+int pn2_rows_bn_finalize(int c, int nparts, const double *partials, long long rows, double eps, const float *weight,
+                         const float *bias, float momentum, float *running_mean, float *running_var, float *a, float *b,
+                         double *stat, pn2_stream_t stream);
+int pn2_rows_bn_bwd_finalize(int c, int nparts, const double *partials, long long rows, const double *stat,
+                             const float *weight, float *k1, float *k2, float *k3, float *dgamma, float *dbeta,
+                             pn2_stream_t stream);
+int pn2_rows_bn_relu_apply(long long rows, int c, const float *x, const float *a, const float *b, float *y,
+                           pn2_stream_t stream);
+int pn2_rows_bn_relu_pool(long long groups, int nsample, int c, const float *x, const float *a, const float *b,
+                          float *pooled, unsigned char *arg, pn2_stream_t stream);
+int pn2_rows_bn_relu_bwd_reduce(long long rows, int c, const float *dy, const float *x, const float *a, const float *b,
+                                double *partials, int *nparts, pn2_stream_t stream);
+int pn2_rows_bn_relu_bwd_apply(long long rows, int c, const float *dy, const float *x, const float *a, const float *b,
+                               const float *k1, const float *k2, const float *k3, float *dx, pn2_stream_t stream);
+int pn2_rows_bn_relu_pool_bwd_reduce(long long groups, int nsample, int c, const float *dpooled, const float *x,
+                                     const unsigned char *arg, const float *a, const float *b, double *partials,
+                                     int *nparts, pn2_stream_t stream);
+int pn2_rows_bn_relu_pool_bwd_apply(long long groups, int nsample, int c, const float *dpooled, const float *x,
+                                    const unsigned char *arg, const float *a, const float *b, const float *k1,
+                                    const float *k2, const float *k3, float *dx, pn2_stream_t stream);
+
+#pragma GCC visibility pop
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,16 @@ oa, ob = a({"point_clouds": pc}), b({"point_clouds": pc})
 la, lb = oa["fp2_features"].square().mean(), ob["fp2_features"].square().mean()
 la.backward(); lb.backward()
 print("loss", float(la), float(lb))
+# a second run of the reference wiring itself: its scatter-adds are float atomics, so it differs from ITSELF run to run
+b2 = copy.deepcopy(net).train()
+b2.train_layout = "reference"
+lb2 = b2({"point_clouds": pc})["fp2_features"].square().mean()
+lb2.backward()
+self_rows = []
+for (n1, p1), (_, p2) in zip(b2.named_parameters(), b.named_parameters()):
+    d = (p1.grad - p2.grad)
+    self_rows.append((float(d.abs().max()) / (float(p2.grad.abs().max()) + 1e-30), float(d.norm() / (p2.grad.norm() + 1e-30)), n1))
+print("reference wiring vs itself: worst max-rel %.3e (%s), worst l2-rel %.3e" % (max(self_rows)[0], max(self_rows)[2], max(r[1] for r in self_rows)))
 rows = []
 for (n1, p1), (_, p2) in zip(a.named_parameters(), b.named_parameters()):
     d = (p1.grad - p2.grad)

@@ -30,6 +30,7 @@ lib = _load()
 _p = c_void_p
 _i = c_int
 _f = c_float
+_ll = ctypes.c_longlong
 
 # name -> (restype, argtypes); mirrors include/pn2_b200.h declaration by declaration
 _PROTOTYPES = {
@@ -60,6 +61,17 @@ _PROTOTYPES = {
     "pn2_ball_query_ws": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, _p, c_size_t, _p]),
     "pn2_ball_query_grid_build": (_i, [_i, _i, _i, _f, _i, _p, _i, _p, c_size_t, _p]),
     "pn2_ball_query_grid_query": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, c_size_t, _p]),
+    "pn2_rows_bn_supported": (_i, [_ll, _i, _i]),
+    "pn2_rows_bn_partials_bytes": (c_size_t, [_ll, _i]),
+    "pn2_rows_bn_stats": (_i, [_ll, _i, _p, _p, POINTER(_i), _p]),
+    "pn2_rows_bn_finalize": (_i, [_i, _i, _p, _ll, ctypes.c_double, _p, _p, _f, _p, _p, _p, _p, _p, _p]),
+    "pn2_rows_bn_bwd_finalize": (_i, [_i, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_rows_bn_relu_apply": (_i, [_ll, _i, _p, _p, _p, _p, _p]),
+    "pn2_rows_bn_relu_pool": (_i, [_ll, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "pn2_rows_bn_relu_bwd_reduce": (_i, [_ll, _i, _p, _p, _p, _p, _p, POINTER(_i), _p]),
+    "pn2_rows_bn_relu_bwd_apply": (_i, [_ll, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pn2_rows_bn_relu_pool_bwd_reduce": (_i, [_ll, _i, _i, _p, _p, _p, _p, _p, _p, POINTER(_i), _p]),
+    "pn2_rows_bn_relu_pool_bwd_apply": (_i, [_ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pn2_group_points": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "pn2_group_points_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "pn2_mlp_f32_image_bytes": (c_size_t, [_i, POINTER(_i)]),

@@ -163,6 +163,14 @@ class Pointnet2Backbone(nn.Module):
         data_dict["fp2_inds"] = inds[0][:, 0:cxyz[1].shape[1]]
         return data_dict
 
+    def prefetch_sampling(self, point_clouds):
+        """Training: start the FPS chain of a FUTURE batch now, on the sampling side stream (it needs the coordinates
+        only).  Called after this step's forward and before its backward, the next batch's 1.9 ms of dependent sampling
+        rounds run under the backward pass; the next ``forward`` on that same tensor picks the result up."""
+        if self.training and self.train_layout == "rows" and point_clouds.is_cuda and point_clouds.dtype == torch.float32:
+            from . import train_rows
+            train_rows._PREFETCHED[self] = train_rows.SamplingPyramid(self, point_clouds.contiguous())
+
     def forward(self, data_dict):
         r"""Reads ``data_dict["point_clouds"]`` (B, N, 3 + input_feature_dim) and adds
         ``sa{1..4}_{xyz,features,inds}``, ``fp2_features`` (B,256,1024), ``fp2_xyz``, ``fp2_inds``."""

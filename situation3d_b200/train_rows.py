@@ -11,10 +11,15 @@ centre's ``nsample`` consecutive rows.  Indices come from this library's samplin
 reference's are cuDNN's.  Parameters and buffers are the modules' own (same names, same state_dict), BatchNorm
 running statistics are updated exactly as ``nn.BatchNorm2d`` would.
 """
+import ctypes
+import os
+import weakref
+
 import torch
 import torch.nn.functional as F
 
 from . import fused as _fused
+from ._lib import check, lib, ptr, stream_ptr
 
 
 def rows_supported(mlp):
@@ -31,12 +36,114 @@ def rows_supported(mlp):
     return True
 
 
-def shared_mlp_rows(mlp, x):
-    """SharedMLP (pytorch_utils.py:11-36) applied to (rows, Cin) instead of (B, Cin, npoint, nsample)."""
-    for layer in mlp:
+class _BnReluRows(torch.autograd.Function):
+    """Training-mode BatchNorm (batch statistics, biased variance) + ReLU [+ max over each group of ``pool_ns`` consecutive
+    rows] on a (rows, C) matrix: csrc/train_rows.cu.  ``running_mean`` / ``running_var`` (or None) are updated in place
+    as nn.BatchNorm2d does.  Nothing but ``x`` is kept for the backward pass (the ReLU mask is recomputed from it)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, pool_ns, momentum, running_mean, running_var):
+        R, C = x.shape
+        dev = x.device
+        partials = torch.empty(lib.pn2_rows_bn_partials_bytes(R, C) // 8, dtype=torch.float64, device=dev)
+        coef = torch.empty((2, C), dtype=torch.float32, device=dev)          # a | b
+        stat = torch.empty((2, C), dtype=torch.float64, device=dev)          # mean | invstd
+        nparts = ctypes.c_int(0)
+        w, b_ = weight.detach().contiguous(), bias.detach().contiguous()
+        with torch.cuda.device(dev):
+            check(lib.pn2_rows_bn_stats(R, C, ptr(x), ptr(partials), ctypes.byref(nparts), stream_ptr()), "rows_bn_stats")
+            check(lib.pn2_rows_bn_finalize(C, nparts.value, ptr(partials), R, float(eps), ptr(w), ptr(b_), float(momentum),
+                                           ptr(running_mean), ptr(running_var), ptr(coef[0]), ptr(coef[1]), ptr(stat),
+                                           stream_ptr()), "rows_bn_finalize")
+            if pool_ns:
+                groups = R // pool_ns
+                out = torch.empty((groups, C), dtype=torch.float32, device=dev)
+                arg = torch.empty((groups, C), dtype=torch.uint8, device=dev)
+                check(lib.pn2_rows_bn_relu_pool(groups, pool_ns, C, ptr(x), ptr(coef[0]), ptr(coef[1]), ptr(out), ptr(arg),
+                                                stream_ptr()), "rows_bn_relu_pool")
+            else:
+                out = torch.empty_like(x)
+                arg = None
+                check(lib.pn2_rows_bn_relu_apply(R, C, ptr(x), ptr(coef[0]), ptr(coef[1]), ptr(out), stream_ptr()),
+                      "rows_bn_relu_apply")
+        ctx.pool_ns = pool_ns
+        ctx.save_for_backward(x, w, coef, stat, arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, coef, stat, arg = ctx.saved_tensors
+        R, C = x.shape
+        dev = x.device
+        dout = dout.contiguous()
+        partials = torch.empty(lib.pn2_rows_bn_partials_bytes(R, C) // 8, dtype=torch.float64, device=dev)
+        k = torch.empty((5, C), dtype=torch.float32, device=dev)             # k1 | k2 | k3 | dgamma | dbeta
+        dx = torch.empty_like(x)
+        nparts = ctypes.c_int(0)
+        ns = ctx.pool_ns
+        a, b = ptr(coef[0]), ptr(coef[1])
+        with torch.cuda.device(dev):
+            if ns:
+                check(lib.pn2_rows_bn_relu_pool_bwd_reduce(R // ns, ns, C, ptr(dout), ptr(x), ptr(arg), a, b, ptr(partials),
+                                                           ctypes.byref(nparts), stream_ptr()), "rows_bn_relu_pool_bwd_reduce")
+            else:
+                check(lib.pn2_rows_bn_relu_bwd_reduce(R, C, ptr(dout), ptr(x), a, b, ptr(partials), ctypes.byref(nparts),
+                                                      stream_ptr()), "rows_bn_relu_bwd_reduce")
+            check(lib.pn2_rows_bn_bwd_finalize(C, nparts.value, ptr(partials), R, ptr(stat), ptr(w), ptr(k[0]), ptr(k[1]),
+                                               ptr(k[2]), ptr(k[3]), ptr(k[4]), stream_ptr()), "rows_bn_bwd_finalize")
+            if ns:
+                check(lib.pn2_rows_bn_relu_pool_bwd_apply(R // ns, ns, C, ptr(dout), ptr(x), ptr(arg), a, b, ptr(k[0]), ptr(k[1]),
+                                                          ptr(k[2]), ptr(dx), stream_ptr()), "rows_bn_relu_pool_bwd_apply")
+            else:
+                check(lib.pn2_rows_bn_relu_bwd_apply(R, C, ptr(dout), ptr(x), a, b, ptr(k[0]), ptr(k[1]), ptr(k[2]), ptr(dx),
+                                                     stream_ptr()), "rows_bn_relu_bwd_apply")
+        return dx, k[3], k[4], None, None, None, None, None
+
+
+def _fused_bn_relu_ok(layer, x, pool_ns):
+    """The hand-written kernels cover what SharedMLP builds: affine BatchNorm2d in training mode followed by ReLU, fp32
+    CUDA rows, channel counts the kernels' thread layout divides."""
+    if not (hasattr(layer, "bn") and hasattr(layer, "activation")) or os.environ.get("PN2_TRAIN_FUSED_BN", "1") == "0":
+        return False
+    bn = layer.bn.bn
+    if not bn.training or bn.weight is None or bn.bias is None:
+        return False
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+        return False
+    R, C = x.shape
+    if pool_ns and R % pool_ns:
+        return False
+    return bool(lib.pn2_rows_bn_supported(R, C, int(pool_ns)))
+
+
+def shared_mlp_rows(mlp, x, pool_ns=0, first_linear_done=False):
+    """SharedMLP (pytorch_utils.py:11-36) applied to (rows, Cin) instead of (B, Cin, npoint, nsample).  With ``pool_ns``
+    the max over each group of ``pool_ns`` consecutive rows (pointnet2_modules.py:259-262) is taken after the last layer
+    and (groups, Cout) is returned.  ``first_linear_done``: x already is the first layer's convolution output."""
+    layers = list(mlp)
+    for li, layer in enumerate(layers):
         conv = layer.conv
-        x = F.linear(x, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
-        if hasattr(layer, "bn"):
+        if not (first_linear_done and li == 0):
+            x = F.linear(x, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
+        pool_here = pool_ns if li == len(layers) - 1 else 0
+        if _fused_bn_relu_ok(layer, x, pool_here):
+            bn = layer.bn.bn
+            track = bn.track_running_stats and bn.running_mean is not None
+            f = 0.0
+            if track:
+                bn.num_batches_tracked.add_(1)
+                f = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
+            x = _BnReluRows.apply(x.contiguous(), bn.weight, bn.bias, float(bn.eps), int(pool_here), f,
+                                  bn.running_mean if track else None, bn.running_var if track else None)
+            continue
+        if hasattr(layer, "bn") and layer.bn.bn.training and os.environ.get("PN2_TRAIN_FUSED_BN") == "2":
+            # diagnostic (scripts/train_parity_diag.py): the same BatchNorm written as x*a + b in plain torch ops --
+            # equivalent arithmetic, different rounding -- to tell rounding sensitivity from a kernel defect
+            bn = layer.bn.bn
+            mean, var = x.mean(dim=0), x.var(dim=0, unbiased=False)
+            a_ = bn.weight * torch.rsqrt(var + bn.eps)
+            x = x * a_ + (bn.bias - mean * a_)
+        elif hasattr(layer, "bn"):
             bn = layer.bn.bn
             factor = 0.0
             if bn.training and bn.track_running_stats:
@@ -47,28 +154,89 @@ def shared_mlp_rows(mlp, x):
                              bn.weight, bn.bias, bn.training or bn.running_mean is None, factor, bn.eps)
         if hasattr(layer, "activation"):
             x = F.relu(x)
+        if pool_here:
+            x = x.view(x.shape[0] // pool_here, pool_here, x.shape[1]).amax(dim=1)
     return x
 
 
-def sa_rows(m, xyz, rows):
+_SIDE_STREAMS = {}
+_PREFETCHED = weakref.WeakKeyDictionary()      # net -> SamplingPyramid started by Pointnet2Backbone.prefetch_sampling
+
+
+class SamplingPyramid:
+    """The FPS chain of the four SA levels for one batch, enqueued on a side stream: it needs the coordinates only,
+    so SA1's dense algebra overlaps the sampling of SA2-SA4, and ``Pointnet2Backbone.prefetch_sampling(next_batch)``
+    lets the whole chain of the NEXT batch run under this batch's backward pass.  ``ready[l]`` is recorded when level
+    l's indices and centres are complete; consumers wait for it on their own stream."""
+
+    def __init__(self, net, pc):
+        from .streams import sampling_stream
+        mods = (net.sa1, net.sa2, net.sa3, net.sa4)
+        B, N, W = pc.shape
+        dev = pc.device
+        self.source = pc
+        self.xyz = torch.empty((B, N, 3), dtype=torch.float32, device=dev)      # filled by the first sampling kernel
+        self.inds = [torch.empty((B, m.npoint), dtype=torch.int32, device=dev) for m in mods]
+        self.cxyz = [torch.empty((B, m.npoint, 3), dtype=torch.float32, device=dev) for m in mods]
+        self.ready = [torch.cuda.Event() for _ in mods]
+        main = torch.cuda.current_stream(dev)
+        side = _SIDE_STREAMS.get(dev.index)        # one per device; kept off the module (streams cannot be deep-copied)
+        if side is None:
+            side = _SIDE_STREAMS[dev.index] = sampling_stream(dev)
+        side.wait_stream(main)                     # the batch (and the buffers above) are ready on the caller's stream
+        with torch.cuda.stream(side), torch.no_grad():
+            src = None
+            for lvl in range(len(mods)):
+                if lvl == 0:
+                    _fused.fps_rows_into(pc, self.inds[0], self.cxyz[0], self.xyz)
+                else:
+                    _fused.fps_into(src, self.inds[lvl], self.cxyz[lvl])
+                self.ready[lvl].record(side)
+                src = self.cxyz[lvl]
+        for t in [pc, self.xyz] + self.inds + self.cxyz:
+            t.record_stream(side)
+
+    def matches(self, pc):
+        return pc is self.source or (pc.data_ptr() == self.source.data_ptr() and pc.shape == self.source.shape and
+                                     pc._version == self.source._version)
+
+
+def sa_rows(m, xyz, rows, sampled=None):
     """PointnetSAModuleVotes.forward (pointnet2_modules.py:210-277, max pooling) on rows (B, N, C).
+    ``sampled`` = (inds, new_xyz) already computed (SamplingPyramid).
     Returns (new_xyz (B,np,3), out_rows (B,np,Cout), inds (B,np) i32)."""
     B, N, _ = xyz.shape
     with torch.no_grad():
-        inds, new_xyz = _fused.fps_with_xyz(xyz, m.npoint)
+        inds, new_xyz = sampled if sampled is not None else _fused.fps_with_xyz(xyz, m.npoint)
         idx = _fused.ball_query(xyz, new_xyz, m.radius, m.nsample)
         flat = (idx.long() + (torch.arange(B, device=xyz.device) * N)[:, None, None]).reshape(-1)
         gxyz = xyz.reshape(B * N, 3).index_select(0, flat).view(B, m.npoint, m.nsample, 3) - new_xyz[:, :, None, :]
         if m.normalize_xyz:
             gxyz = gxyz / m.radius                                                   # pointnet2_utils.py:350-351
         gxyz = gxyz.reshape(-1, 3)
-    if rows is not None:
-        g = rows.reshape(B * N, rows.shape[2]).index_select(0, flat)                 # backward: row scatter-add
-        x = torch.cat([gxyz, g], dim=1) if m.use_xyz else g                          # xyz channels first (:355-360)
+    conv0 = m.mlp_module[0].conv
+    if rows is not None and os.environ.get("PN2_TRAIN_SPLIT_L1", "0") == "1":
+        # Layer 1 is linear in [xyz | features[idx]]: the feature part is applied ONCE PER POINT (B*N rows instead of
+        # B*npoint*nsample: 3-16x fewer rows) and the (narrower) products are gathered; the three coordinate columns are
+        # added per sample.  Same sum, different association (as the forward-only path's pn2_lin_tc_forward split);
+        # the (rows, C+3) grouped matrix of the reference (pointnet2_utils.py:355-360) is never built.
+        W = conv0.weight.view(conv0.out_channels, conv0.in_channels)
+        Wf = W[:, 3:] if m.use_xyz else W
+        P = F.linear(rows.reshape(B * N, rows.shape[2]), Wf)                         # (B*N, C1)
+        z = P.index_select(0, flat)                                                  # backward: row scatter-add into dP
+        if m.use_xyz:
+            z = z.addmm_(gxyz, W[:, :3].t())
+        if conv0.bias is not None:
+            z = z + conv0.bias
+        x = shared_mlp_rows(m.mlp_module, z, pool_ns=m.nsample, first_linear_done=True)
     else:
-        x = gxyz
-    x = shared_mlp_rows(m.mlp_module, x)
-    out_rows = x.view(B * m.npoint, m.nsample, x.shape[1]).amax(dim=1).view(B, m.npoint, x.shape[1])
+        if rows is not None:
+            g = rows.reshape(B * N, rows.shape[2]).index_select(0, flat)             # backward: row scatter-add
+            x = torch.cat([gxyz, g], dim=1) if m.use_xyz else g                      # xyz channels first (:355-360)
+        else:
+            x = gxyz
+        x = shared_mlp_rows(m.mlp_module, x, pool_ns=m.nsample)
+    out_rows = x.view(B, m.npoint, x.shape[1])
     return new_xyz, out_rows, inds
 
 
@@ -91,11 +259,17 @@ def fp_rows(m, unknown, known, skip_rows, known_rows):
 
 def backbone_forward_rows(net, pc, data_dict):
     """Pointnet2Backbone.forward in training mode over rows; same dictionary keys as the other paths."""
-    xyz = pc[..., :3].contiguous()
+    pyr = _PREFETCHED.pop(net, None)
+    if pyr is None or not pyr.matches(pc):
+        pyr = SamplingPyramid(net, pc.contiguous())
+    main = torch.cuda.current_stream(pc.device)
+    main.wait_event(pyr.ready[0])
+    xyz = pyr.xyz
     rows = pc[..., 3:] if pc.shape[2] > 3 else None
     level_xyz, level_rows = [], []
     for lvl, m in enumerate((net.sa1, net.sa2, net.sa3, net.sa4), start=1):
-        xyz, rows, inds = sa_rows(m, xyz, rows)
+        main.wait_event(pyr.ready[lvl - 1])
+        xyz, rows, inds = sa_rows(m, xyz, rows, sampled=(pyr.inds[lvl - 1], pyr.cxyz[lvl - 1]))
         level_xyz.append(xyz)
         level_rows.append(rows)
         data_dict["sa%d_inds" % lvl] = inds

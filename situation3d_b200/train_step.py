@@ -26,11 +26,14 @@ class BackboneTrainer:
         if self.overlap:
             self.bucket.enable_overlap(3, self.comm_stream)
 
-    def step(self, point_clouds):
-        """One step on this rank's scenes; returns the (local) loss tensor."""
+    def step(self, point_clouds, next_point_clouds=None):
+        """One step on this rank's scenes; returns the (local) loss tensor.  ``next_point_clouds`` (the batch the data
+        loader already holds for the following step) has its sampling chain started under this step's backward."""
         self.bucket.zero()
         out = self.net({"point_clouds": point_clouds})
         loss = out["fp2_features"].square().mean()
+        if next_point_clouds is not None and hasattr(self.net, "prefetch_sampling"):
+            self.net.prefetch_sampling(next_point_clouds)
         loss.backward()                                   # gradients land in the flat bucket; chunk hooks start the collectives
         if self.overlap:
             self.bucket.finish()

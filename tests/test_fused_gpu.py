@@ -521,6 +521,38 @@ def test_row_layout_training_matches_reference_wiring():
             assert torch.equal(t1, t2), n1
 
 
+@pytest.mark.parametrize("groups,ns,c", [(4096, 0, 64), (300, 16, 128), (257, 32, 256), (1000, 64, 64), (50, 1, 128)])
+def test_rows_bn_relu_pool_kernels_match_torch_autograd(groups, ns, c):
+    """csrc/train_rows.cu (training-mode BatchNorm + ReLU [+ max over nsample] on rows, forward and backward) against
+    the reference's chain BatchNorm2d -> ReLU -> max_pool2d under torch autograd, duplicated rows (ball-query padding:
+    exact ties in the max) included."""
+    import torch.nn.functional as F
+    from situation3d_b200.train_rows import _BnReluRows
+    g = torch.Generator().manual_seed(groups + ns + c)
+    rows = groups * max(ns, 1)
+    x = (torch.randn(rows, c, generator=g) * 2.0 + torch.randn(c, generator=g)).cuda()
+    if ns > 1:
+        x.view(groups, ns, c)[::3, ns // 2:] = x.view(groups, ns, c)[::3, :1]          # padded copies of the first neighbour
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).cuda(), torch.randn(c, generator=g).cuda()
+    xa, ga, ba = (t.clone().requires_grad_(True) for t in (x, gamma, beta))
+    xb, gb, bb = (t.clone().requires_grad_(True) for t in (x, gamma, beta))
+    rm0, rv0 = torch.randn(c, generator=g).cuda(), (torch.rand(c, generator=g) + 0.5).cuda()
+    rm, rv, rma, rva = rm0.clone(), rv0.clone(), rm0.clone(), rv0.clone()
+    out = _BnReluRows.apply(xa, ga, ba, 1e-5, ns, 0.1, rma, rva)
+    y = F.relu(F.batch_norm(xb, rm, rv, gb, bb, True, 0.1, 1e-5))
+    if ns:
+        y = F.max_pool2d(y.view(1, groups, ns, c).permute(0, 3, 1, 2), kernel_size=[1, ns]).squeeze(3).squeeze(0).t()
+    torch.testing.assert_close(out, y, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rma, rm, rtol=1e-5, atol=1e-6)           # running statistics, as nn.BatchNorm2d updates them
+    torch.testing.assert_close(rva, rv, rtol=1e-5, atol=1e-6)
+    dout = torch.randn(out.shape, generator=g).cuda()
+    out.backward(dout)
+    y.backward(dout)
+    for got, want, name in ((xa.grad, xb.grad, "dx"), (ga.grad, gb.grad, "dgamma"), (ba.grad, bb.grad, "dbeta")):
+        scale = float(want.abs().max()) + 1e-12
+        assert float((got - want).abs().max()) <= 2e-5 * scale + 1e-6, name
+
+
 def test_compact_input_is_bit_identical():
     """fp32 coordinates + bf16 feature rows (Pointnet2Backbone.pack_point_clouds: half the host-to-device bytes) give
     bit-identical results to the reference's fp32 point_clouds on the bf16 arm, eagerly and through the pipeline from
