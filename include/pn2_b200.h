@@ -456,6 +456,13 @@ int pn2_rows_bn_relu_pool_bwd_apply(long long groups, int nsample, int c, const 
                                     const unsigned char *arg, const float *a, const float *b, const float *k1,
                                     const float *k2, const float *k3, float *dx, pn2_stream_t stream);
 
+/* The grouped input matrix of an SA module in the row layout, one pass: out (b*npoint*nsample, c+3) =
+ * [ (xyz[idx] - centre) (/ radius if normalize_xyz) | rows[idx] ], xyz channels first -- QueryAndGroup's group(xyz), -=, /=,
+ * group(features), cat (lib/pointnet2/pointnet2_utils.py:348-359).  idx (b, npoint, nsample) scene-local; rows (b, n, ld). */
+int pn2_group_rows(int b, int n, int npoint, int nsample, int c, int ld, const int *idx, const float *xyz,
+                   const float *new_xyz, const float *rows, float radius, int normalize_xyz, float *out,
+                   pn2_stream_t stream);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

@@ -8,7 +8,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpn2_b200.so")
+LIB_PATH = os.environ.get("PN2_B200_LIB") or os.path.join(_HERE, "libpn2_b200.so")   # PN2_B200_LIB: an A/B build (build.py)
 
 PN2_OK = 0
 
@@ -61,6 +61,7 @@ _PROTOTYPES = {
     "pn2_ball_query_ws": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, _p, c_size_t, _p]),
     "pn2_ball_query_grid_build": (_i, [_i, _i, _i, _f, _i, _p, _i, _p, c_size_t, _p]),
     "pn2_ball_query_grid_query": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, c_size_t, _p]),
+    "pn2_group_rows": (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _i, _p, _p]),
     "pn2_rows_bn_supported": (_i, [_ll, _i, _i]),
     "pn2_rows_bn_partials_bytes": (c_size_t, [_ll, _i]),
     "pn2_rows_bn_stats": (_i, [_ll, _i, _p, _p, POINTER(_i), _p]),

@@ -13,8 +13,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpn2_b200.so")
-OBJ_DIR = os.path.join(HERE, "csrc", "build")
+# PN2_BUILD_SUFFIX / PN2_BUILD_DEFINES: a second library next to the default one, compiled with extra -D switches, for
+# A/B measurements on the GPU box (loaded through PN2_B200_LIB, see _lib.py); the default build ignores both
+SUFFIX = os.environ.get("PN2_BUILD_SUFFIX", "")
+LIB = os.path.join(HERE, "libpn2_b200%s.so" % SUFFIX)
+OBJ_DIR = os.path.join(HERE, "csrc", "build" + SUFFIX)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 NVCC_FLAGS = [
@@ -22,7 +25,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("PN2_BUILD_DEFINES", "").split()
 
 
 def sources():

@@ -71,10 +71,28 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+// Suspend-time hint of try_wait: the warp sleeps in hardware until the phase completes (or the hint expires) instead
+// of re-issuing the probe.  Without it a round of the cluster kernel spent ~10 probe + branch pairs (8 % of its
+// instructions) spinning -- issue slots the co-resident CTA of another scene could use.
+#ifndef PN2_FPS_MBAR_HINT
+#define PN2_FPS_MBAR_HINT 0x989680u
+#endif
+constexpr uint32_t kMbarSuspendHint = PN2_FPS_MBAR_HINT;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done;
     do {
+#if PN2_FPS_MBAR_HINT
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(kMbarSuspendHint)
+            : "memory");
+#else
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -84,6 +102,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
+#endif
     } while (!done);
 }
 // 16-byte / 4-byte store into a peer CTA's shared memory that also completes `bytes` on the
@@ -187,7 +206,8 @@ fps_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int 
     __shared__ __align__(16) uint4 table[2][kMaxCluster * kMaxWarps];
     __shared__ __align__(8) uint64_t bar[2];
 
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    // the 40-slot variant is only ever launched with MAXT threads: a compile-time T folds the slot addressing
+    const int T = (P == 40) ? MAXT : (int)blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const uint32_t C = CLUSTER ? cluster_nctarank() : 1u, rank = CLUSTER ? cluster_ctarank() : 0u;
     const int scene = blockIdx.x / C;
     const float *p = xyz + (size_t)scene * n * pitch;       // rows of `pitch` floats, xyz first (pitch = 3: plain (n,3))

@@ -11,15 +11,29 @@ __device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes instead of re-issuing
+// the probe + branch, which leaves its issue slots to the warps that have work (the producer / issuer / epilogue warps
+// of these kernels share four schedulers).  -DPN2_TC_MBAR_HINT=0 builds the plain spinning form (A/B measurements).
+#ifndef PN2_TC_MBAR_HINT
+#define PN2_TC_MBAR_HINT 0x989680
+#endif
 __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done;
     do {
+#if PN2_TC_MBAR_HINT
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"((uint32_t)PN2_TC_MBAR_HINT) : "memory");
+#else
         asm volatile(
             "{\n.reg .pred p;\n"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
     } while (!done);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

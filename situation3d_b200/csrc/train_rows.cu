@@ -319,6 +319,34 @@ bn_relu_pool_bwd_apply_kernel(long long groups, int ns, int c, const float *__re
     }
 }
 
+
+// Grouped input matrix of an SA module, built in one pass: out[r] = [ (xyz[idx[r]] - centre[r / ns]) / radius | rows[idx[r]] ]
+// (QueryAndGroup: pointnet2_utils.py:348-359 -- grouped_xyz -= centre, /= radius, xyz channels first).
+// idx holds scene-local indices; r runs over (scene, centre, sample).  One warp per output row, consecutive lanes on
+// consecutive channels (coalesced reads of the source row and writes of the output row).
+__global__ void __launch_bounds__(kTrThreads)
+group_rows_kernel(long long total_rows, int n, int per_scene, int ns, int c, int ld, const int *__restrict__ idx,
+                  const float *__restrict__ xyz, const float *__restrict__ centres, const float *__restrict__ rows,
+                  float radius, int normalize, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = c + 3;
+    for (long long r = (long long)blockIdx.x * (kTrThreads / 32) + (threadIdx.x >> 5); r < total_rows;
+         r += (long long)gridDim.x * (kTrThreads / 32)) {
+        const long long scene = r / per_scene;
+        const long long src = scene * n + __ldg(idx + r);
+        float *o = out + r * w;
+        if (lane < 3) {
+            float d = __fsub_rn(__ldg(xyz + src * 3 + lane), __ldg(centres + (r / ns) * 3 + lane));
+            // torch divides a CUDA tensor by a Python scalar as a multiplication by the fp32 reciprocal (BinaryDivTrueKernel)
+            if (normalize) d = __fmul_rn(d, __fdiv_rn(1.f, radius));
+            o[lane] = d;
+        }
+        const float *p = rows + src * ld;
+        for (int j = lane; j < c; j += 32) o[3 + j] = __ldg(p + j);
+    }
+}
+
 static bool shape_ok(long long rows, int c) { return rows >= 0 && c >= 4 && c % 4 == 0 && c <= 1024 && kTrThreads % (c / 4) == 0; }
 
 // CTAs of a reduction over `rows` (= slots of its partials buffer): at most two per SM, never more than there are
@@ -460,5 +488,23 @@ extern "C" int pn2_rows_bn_relu_pool_bwd_apply(long long groups, int nsample, in
     bn_relu_pool_bwd_apply_kernel<<<flat_grid(groups * (c / 4), s), kTrThreads, 0, s>>>(groups, nsample, c, dpooled, x, arg, a, b,
                                                                                       k1, k2, k3, dx);
     PN2_LAUNCH_CHECK("rows_bn_relu_pool_bwd_apply");
+    return PN2_OK;
+}
+
+// out (b*npoint*nsample, c+3) = [normalised relative xyz | gathered feature rows]; rows: (b, n, ld) with c <= ld
+extern "C" int pn2_group_rows(int b, int n, int npoint, int nsample, int c, int ld, const int *idx, const float *xyz,
+                              const float *new_xyz, const float *rows, float radius, int normalize_xyz, float *out,
+                              pn2_stream_t stream)
+{
+    if (b < 0 || n < 1 || npoint < 0 || nsample < 1 || c < 0 || ld < c) return PN2_ERR_INVALID_ARGUMENT;
+    const long long total = (long long)b * npoint * nsample;
+    if (total == 0) return PN2_OK;
+    if (!idx || !xyz || !new_xyz || !out || (c > 0 && !rows)) return PN2_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = as_stream(stream);
+    const long long want = (total + kTrThreads / 32 - 1) / (kTrThreads / 32);
+    const int grid = (int)max(1LL, min(want, (long long)stream_sm_count(s) * 16));
+    group_rows_kernel<<<grid, kTrThreads, 0, s>>>(total, n, npoint * nsample, nsample, c, ld, idx, xyz, new_xyz, rows, radius,
+                                                  normalize_xyz, out);
+    PN2_LAUNCH_CHECK("group_rows");
     return PN2_OK;
 }

@@ -100,6 +100,41 @@ class _BnReluRows(torch.autograd.Function):
         return dx, k[3], k[4], None, None, None, None, None
 
 
+class _GroupRows(torch.autograd.Function):
+    """QueryAndGroup on rows (pointnet2_utils.py:348-359) in one pass: (rows, C+3) = [normalised relative xyz | features of
+    the neighbours].  Backward: row scatter-add of the feature columns (the coordinates carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, rows, xyz, new_xyz, idx, radius, normalize):
+        B, N, ld = rows.shape[0], rows.shape[1], rows.stride(1)
+        C = rows.shape[2]
+        npoint, ns = idx.shape[1], idx.shape[2]
+        out = torch.empty((B * npoint * ns, C + 3), dtype=torch.float32, device=rows.device)
+        with torch.cuda.device(rows.device):
+            check(lib.pn2_group_rows(B, N, npoint, ns, C, ld, ptr(idx), ptr(xyz), ptr(new_xyz), ptr(rows), float(radius),
+                                     int(bool(normalize)), ptr(out), stream_ptr()), "group_rows")
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, N, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None, None
+        (idx,) = ctx.saved_tensors
+        B, N, C = ctx.shape
+        flat = (idx.long() + (torch.arange(B, device=idx.device) * N)[:, None, None]).reshape(-1)
+        d = torch.zeros((B * N, C), dtype=dout.dtype, device=dout.device)
+        d.index_add_(0, flat, dout[:, 3:])
+        return d.view(B, N, C), None, None, None, None, None
+
+
+def _group_rows_ok(rows, xyz):
+    """rows (B, N, C) fp32 CUDA whose rows are contiguous (a column slice of point_clouds qualifies: pitch = stride(1))."""
+    return (rows is not None and rows.is_cuda and rows.dtype == torch.float32 and rows.dim() == 3 and rows.stride(2) == 1 and
+            rows.stride(0) == rows.shape[1] * rows.stride(1) and os.environ.get("PN2_TRAIN_GROUP_KERNEL", "1") != "0")
+
+
 def _fused_bn_relu_ok(layer, x, pool_ns):
     """The hand-written kernels cover what SharedMLP builds: affine BatchNorm2d in training mode followed by ReLU, fp32
     CUDA rows, channel counts the kernels' thread layout divides."""
@@ -229,6 +264,9 @@ def sa_rows(m, xyz, rows, sampled=None):
         if conv0.bias is not None:
             z = z + conv0.bias
         x = shared_mlp_rows(m.mlp_module, z, pool_ns=m.nsample, first_linear_done=True)
+    elif m.use_xyz and _group_rows_ok(rows, xyz):
+        x = _GroupRows.apply(rows, xyz, new_xyz, idx, m.radius, m.normalize_xyz)
+        x = shared_mlp_rows(m.mlp_module, x, pool_ns=m.nsample)
     else:
         if rows is not None:
             g = rows.reshape(B * N, rows.shape[2]).index_select(0, flat)             # backward: row scatter-add

@@ -553,6 +553,36 @@ def test_rows_bn_relu_pool_kernels_match_torch_autograd(groups, ns, c):
         assert float((got - want).abs().max()) <= 2e-5 * scale + 1e-6, name
 
 
+def test_group_rows_kernel_matches_query_and_group_on_rows():
+    """pn2_group_rows (one pass) against the torch formulation of QueryAndGroup on rows (index_select, -=, /=, cat),
+    forward bit for bit, backward = row scatter-add of the feature columns; source rows taken as a column slice of a
+    wider matrix (point_clouds[..., 3:]) and as a contiguous tensor."""
+    from situation3d_b200 import fused
+    from situation3d_b200.train_rows import _GroupRows
+    g = torch.Generator().manual_seed(5)
+    B, N, C, npoint, ns, radius = 2, 3000, 9, 128, 16, 0.3
+    pc = torch.randn(B, N, 3 + C, generator=g).cuda()
+    xyz = pc[..., :3].contiguous()
+    inds, new_xyz = fused.fps_with_xyz(xyz, npoint)
+    idx = fused.ball_query(xyz, new_xyz, radius, ns)
+    flat = (idx.long() + (torch.arange(B, device="cuda") * N)[:, None, None]).reshape(-1)
+    for rows in (pc[..., 3:], pc[..., 3:].contiguous()):
+        for normalize in (True, False):
+            ra = rows.detach().clone().requires_grad_(True) if rows.is_contiguous() else rows
+            got = _GroupRows.apply(ra, xyz, new_xyz, idx, radius, normalize)
+            gx = xyz.reshape(B * N, 3).index_select(0, flat).view(B, npoint, ns, 3) - new_xyz[:, :, None, :]
+            if normalize:
+                gx = gx / radius
+            rb = rows.detach().clone().requires_grad_(True)
+            want = torch.cat([gx.reshape(-1, 3), rb.reshape(B * N, C).index_select(0, flat)], dim=1)
+            assert torch.equal(got, want)
+            if ra.requires_grad:
+                dout = torch.randn(want.shape, generator=g).cuda()
+                got.backward(dout)
+                want.backward(dout)
+                torch.testing.assert_close(ra.grad, rb.grad, rtol=1e-5, atol=1e-5)
+
+
 def test_compact_input_is_bit_identical():
     """fp32 coordinates + bf16 feature rows (Pointnet2Backbone.pack_point_clouds: half the host-to-device bytes) give
     bit-identical results to the reference's fp32 point_clouds on the bf16 arm, eagerly and through the pipeline from
