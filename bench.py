@@ -47,17 +47,21 @@ sys.path.insert(0, ROOT)
 METRIC = "Pointnet2Backbone scenes/sec (40k pts)"
 UNIT = "scenes/s"
 
-# BASELINE.json configs: per-GPU batch, points, precision, batches in flight, SA pyramid
+# BASELINE.json configs: per-GPU batch, points, precision, batches in flight, SA pyramid.
+# Batches in flight ("lanes", one CUDA stream + graph each) are what fills the GPU: a batch's sampling chains occupy
+# 8 CTAs per scene (one per scene above 81 920 points) for milliseconds.  Measured optima (scripts/gpu_r2_check7.sh):
+# config 2 plateaus at 16-24 (12.8-13.0 k scenes/s; 11.4-12.0 k at 8), config 3 at 24, config 5 still gains at 16 (3.3 k against
+# 1.0 k scenes/s at 2).
 CONFIGS = {
     1: dict(batch=1, points=40000, precision="fp32", lanes=1, npoints=(2048, 1024, 512, 256),
             what="config 1: Pointnet2Backbone forward, one 40 000-point scene, fp32 arm, one batch in flight"),
-    2: dict(batch=8, points=40000, precision="bf16", lanes=8, npoints=(2048, 1024, 512, 256),
+    2: dict(batch=8, points=40000, precision="bf16", lanes=20, npoints=(2048, 1024, 512, 256),
             what="config 2: Pointnet2Backbone forward (SA1-SA4 + FP1-FP2), B=8 scenes/GPU x 40000 points, "
                  "xyz+height+128-d multiview, bf16 fused MLPs (BASELINE configs[1])"),
-    3: dict(batch=4, points=40000, precision="bf16", lanes=8, npoints=(2048, 1024, 512, 256), reencode=True,
+    3: dict(batch=4, points=40000, precision="bf16", lanes=24, npoints=(2048, 1024, 512, 256), reencode=True,
             what="config 3: backbone + situation re-encoding (agent-frame transform + pos_embed + prior) of the first 256 "
                  "seeds, 4 scenes/GPU (32 scenes sharded over 8 GPUs)"),
-    5: dict(batch=8, points=200000, precision="bf16", lanes=2, npoints=(4096, 2048, 1024, 512),
+    5: dict(batch=8, points=200000, precision="bf16", lanes=16, npoints=(4096, 2048, 1024, 512),
             what="config 5: stress, 200 000-point scenes, SA npoint 4096/2048/1024/512, nsample 64/32/16/16, "
                  "8 scenes/GPU (64 scenes over 8 GPUs)"),
 }
@@ -924,7 +928,8 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_sub_configs and args.config == 2:
         for which in (1, 3, 4, 5):
             try:
-                subs[str(which)] = sub_config(args, which, rank, local_rank, world, max(4, min(K, 12)))
+                subs[str(which)] = sub_config(args, which, rank, local_rank, world,
+                                               max(4, min(K, 12)) if which in (1, 4) else 2 * CONFIGS[which]["lanes"])
             except Exception as ex:
                 subs[str(which)] = [{"config": which, "error": repr(ex)[:300]}]
 

@@ -71,11 +71,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-// Suspend-time hint of try_wait: the warp sleeps in hardware until the phase completes (or the hint expires) instead
-// of re-issuing the probe.  Without it a round of the cluster kernel spent ~10 probe + branch pairs (8 % of its
-// instructions) spinning -- issue slots the co-resident CTA of another scene could use.
+// Optional suspend-time hint of try_wait (-DPN2_FPS_MBAR_HINT=0x989680): the warp would sleep in hardware until the
+// phase completes instead of re-issuing the probe (~10 probe + branch pairs per round).  Measured neutral, alone and
+// with two CTAs per SM (1.351 / 1.636 ms against 1.353 / 1.630 ms, scripts/gpu_r2_hint.sh): the default probe already
+// suspends for about as long as the exchange takes.  Off by default.
 #ifndef PN2_FPS_MBAR_HINT
-#define PN2_FPS_MBAR_HINT 0x989680u
+#define PN2_FPS_MBAR_HINT 0
 #endif
 constexpr uint32_t kMbarSuspendHint = PN2_FPS_MBAR_HINT;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
@@ -502,13 +503,17 @@ static int dispatch(const FpsPlan &pl, int b, int n, int m, const float *xyz, in
 #define PN2_FPS_CASE(P, REGS, MAXT) \
     case P: return launch<P, REGS, MAXT>(pl, b, n, m, xyz, pitch, idxs, new_xyz, xyz_copy, prof, s)
     if (pl.threads == 128 && pl.ppt == 40 && pl.cluster > 1) {
-        // PN2_FPS_RP (tuning): slot pairs whose coordinates stay in registers.  6 or 0 -> 168 registers, three CTAs
-        // per SM instead of two.  Measured (scripts/fps_rp_sweep.py, fps_sat_one.py): 48 scenes resident instead of
-        // 32, but +33 % instructions per round (LDS + moves) and a slower round (1.54 vs 1.35 ms alone), so the
-        // saturated throughput is the same within 4 % (0.393 vs 0.408 ms per 8 scenes) -- default stays all-register.
-        static const int rp = [] { const char *e = getenv("PN2_FPS_RP"); return e ? atoi(e) : 20; }();
+        // PN2_FPS_RP: slot pairs whose coordinates stay in registers (default 6 of 20; the others are re-read from the
+        // CTA's shared-memory copy every round).  164 registers instead of 237 -> three CTAs per SM, 48 scenes resident
+        // instead of 32.  Measured (scripts/fps_sat_one.py, gpu_r2_check6.sh): alone 1.38 against 1.35 ms, saturated
+        // 0.356 against 0.409 ms per 8 scenes, bench step +5-8 %.  20 = all in registers (two CTAs per SM).
+        // A single scene is a latency problem (nothing else competes for its 8 SMs): all-register kernel.
+        static const int rp_env = [] { const char *e = getenv("PN2_FPS_RP"); return e ? atoi(e) : -1; }();
+        const int rp = rp_env >= 0 ? rp_env : (b == 1 ? 20 : 6);
         auto kern = rp == 0 ? fps_kernel<40, false, true, 128, 3, 0>
+                  : rp == 4 ? fps_kernel<40, false, true, 128, 3, 4>
                   : rp == 6 ? fps_kernel<40, false, true, 128, 3, 6>
+                  : rp == 8 ? fps_kernel<40, false, true, 128, 3, 8>
                             : fps_kernel<40, true, true, 128, 2>;
         const size_t smem = (size_t)3 * 40 * 128 * sizeof(float);
         PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

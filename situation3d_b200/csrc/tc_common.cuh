@@ -11,11 +11,11 @@ __device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes instead of re-issuing
-// the probe + branch, which leaves its issue slots to the warps that have work (the producer / issuer / epilogue warps
-// of these kernels share four schedulers).  -DPN2_TC_MBAR_HINT=0 builds the plain spinning form (A/B measurements).
+// -DPN2_TC_MBAR_HINT=0x989680 builds try_wait with a suspend-time hint (a waiting warp sleeps in hardware until the phase
+// completes instead of re-issuing the probe + branch).  Measured neutral on every kernel of the step (SA1 59.4 us both
+// ways, scripts/gpu_r2_hint.sh), so the plain form stays the default.
 #ifndef PN2_TC_MBAR_HINT
-#define PN2_TC_MBAR_HINT 0x989680
+#define PN2_TC_MBAR_HINT 0
 #endif
 __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity)
 {
