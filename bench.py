@@ -50,7 +50,7 @@ UNIT = "scenes/s"
 # BASELINE.json configs: per-GPU batch, points, precision, batches in flight, SA pyramid.
 # Batches in flight ("lanes", one CUDA stream + graph each) are what fills the GPU: a batch's sampling chains occupy
 # 8 CTAs per scene (one per scene above 81 920 points) for milliseconds.  Measured optima (scripts/gpu_r2_check7.sh):
-# config 2 plateaus at 16-24 (12.8-13.0 k scenes/s; 11.4-12.0 k at 8), config 3 at 24, config 5 still gains at 16 (3.3 k against
+# config 2 plateaus at 16-24 (12.8-13.0 k scenes/s; 11.4-12.0 k at 8), config 3 at 24, config 5 at 16-24 (3.3 k against
 # 1.0 k scenes/s at 2).
 CONFIGS = {
     1: dict(batch=1, points=40000, precision="fp32", lanes=1, npoints=(2048, 1024, 512, 256),
@@ -61,7 +61,7 @@ CONFIGS = {
     3: dict(batch=4, points=40000, precision="bf16", lanes=24, npoints=(2048, 1024, 512, 256), reencode=True,
             what="config 3: backbone + situation re-encoding (agent-frame transform + pos_embed + prior) of the first 256 "
                  "seeds, 4 scenes/GPU (32 scenes sharded over 8 GPUs)"),
-    5: dict(batch=8, points=200000, precision="bf16", lanes=16, npoints=(4096, 2048, 1024, 512),
+    5: dict(batch=8, points=200000, precision="bf16", lanes=24, npoints=(4096, 2048, 1024, 512),
             what="config 5: stress, 200 000-point scenes, SA npoint 4096/2048/1024/512, nsample 64/32/16/16, "
                  "8 scenes/GPU (64 scenes over 8 GPUs)"),
 }
