@@ -255,11 +255,11 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
         t = timeit(lambda: fused.fps_with_xyz(src_xyz, m.npoint))
         # FPS is a chain of dependent rounds: besides the (meaningless) HBM figure, report rounds/s and the share of the
         # machine the launch occupies (one CTA per scene for large scenes, csrc/fps_bucket.cu)
-        # SMs a sampling launch can occupy: the register-resident cluster kernel (csrc/fps.cu) runs 8 CTAs of 128 threads
-        # per scene, two per SM, for 8 193 .. 81 920 points; one CTA per scene otherwise (small scenes: 256-512 threads,
-        # about half an SM; csrc/fps_bucket.cu beyond)
+        # SMs a sampling launch can occupy: the cluster kernel (csrc/fps.cu) runs 8 CTAs of 128 threads per scene for
+        # 8 193 .. 81 920 points, three per SM (two for a single scene: the all-register variant); one CTA per scene otherwise
+        # (small scenes: 256-512 threads, about half an SM; csrc/fps_bucket.cu beyond)
         if 8192 < n_in <= 81920:
-            sm_share = min(1.0, B * 8 * 0.5 / 148.0)
+            sm_share = min(1.0, B * 8 / (3.0 if B > 1 else 2.0) / 148.0)
         else:
             sm_share = min(1.0, B * (0.5 if n_in <= 8192 else 1.0) / 148.0)
         rows.append({"kernel": "fps_" + name, "bound": "hbm", "seconds": t,
