@@ -86,6 +86,8 @@ def parse():
                     help="batches in flight per GPU: step i runs on CUDA stream i %% lanes (1 = strictly serial steps)")
     ap.add_argument("--fps-sms", type=int, default=0,
                     help="give the sampling chains their own group of >= this many SMs (CUDA green contexts); 0 = off")
+    ap.add_argument("--sampling-mode", default="auto", choices=["auto", "latency", "throughput"],
+                    help="FPS kernel of the captured steps for mid-sized scenes (auto: throughput from 128 scenes in flight)")
     ap.add_argument("--no-graphs", action="store_true",
                     help="enqueue every step from Python instead of replaying a captured CUDA graph per lane")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,9 +218,10 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
-def kernel_breakdown(net, pc, precision, pk, reps=5):
+def kernel_breakdown(net, pc, precision, pk, reps=5, sampling_mode="latency"):
     """Every kernel of one step launched alone through the C ABI and timed with CUDA events on the
-    launching (current) stream; algorithmic bytes / FLOPs per launch as defined in DESIGN.md."""
+    launching (current) stream; algorithmic bytes / FLOPs per launch as defined in DESIGN.md.  ``sampling_mode``: the
+    FPS kernel the timed step used (fused.sampling_mode), so that the ranking describes that step."""
     import torch
     from situation3d_b200 import fused
     B, N, W = pc.shape
@@ -251,18 +254,23 @@ def kernel_breakdown(net, pc, precision, pk, reps=5):
     for lvl, m in enumerate(sas):
         n_in = src_xyz.shape[1]
         name = "sa%d" % (lvl + 1)
-        inds, cxyz = fused.fps_with_xyz(src_xyz, m.npoint)
-        t = timeit(lambda: fused.fps_with_xyz(src_xyz, m.npoint))
+        with fused.sampling_mode(sampling_mode):
+            inds, cxyz = fused.fps_with_xyz(src_xyz, m.npoint)
+            t = timeit(lambda: fused.fps_with_xyz(src_xyz, m.npoint))
+            bucketed = fused.lib.pn2_furthest_point_sampling_workspace_bytes_mode(B, n_in, m.npoint, fused._SAMPLING_MODE[0]) > 0
         # FPS is a chain of dependent rounds: besides the (meaningless) HBM figure, report rounds/s and the share of the
         # machine the launch occupies (one CTA per scene for large scenes, csrc/fps_bucket.cu)
         # SMs a sampling launch can occupy: the cluster kernel (csrc/fps.cu) runs 8 CTAs of 128 threads per scene for
         # 8 193 .. 81 920 points, three per SM (two for a single scene: the all-register variant); one CTA per scene otherwise
         # (small scenes: 256-512 threads, about half an SM; csrc/fps_bucket.cu beyond)
-        if 8192 < n_in <= 81920:
+        if bucketed:
+            sm_share = min(1.0, B / 148.0)                     # csrc/fps_bucket.cu: one CTA per scene, one per SM
+        elif 8192 < n_in <= 81920:
             sm_share = min(1.0, B * 8 / (3.0 if B > 1 else 2.0) / 148.0)
         else:
             sm_share = min(1.0, B * (0.5 if n_in <= 8192 else 1.0) / 148.0)
-        rows.append({"kernel": "fps_" + name, "bound": "hbm", "seconds": t,
+        rows.append({"kernel": "fps_" + name, "variant": "bucketed, one CTA per scene" if bucketed else "register-resident",
+                     "bound": "hbm", "seconds": t,
                      "alg_bytes": B * (12 * n_in + 16 * m.npoint), "rounds_per_s": (m.npoint - 1) / t,
                      "sm_share": sm_share})
         idx = fused.ball_query(src_xyz, cxyz, m.radius, m.nsample)
@@ -559,10 +567,15 @@ class Runner:
             if not args.no_graphs:
                 # one captured step per lane (situation3d_b200.graphs): replaying it costs the host one cudaGraphLaunch
                 # instead of ~0.8 ms of Python launches, which is what bounds the eager loop once lanes overlap
-                from situation3d_b200.graphs import GraphedBackbone
+                from situation3d_b200.graphs import GraphedBackbone, pick_sampling_mode
+                # which FPS kernel the captured steps use at 40 000 points: the fastest launch, or -- with enough scenes in
+                # flight to give every SM a scene -- the one with the least SM time (identical results; fused.sampling_mode)
+                self.sampling_mode = (args.sampling_mode if args.sampling_mode != "auto"
+                                      else pick_sampling_mode(nl * self.cfg["batch"]))
                 try:
                     self.graphs = [GraphedBackbone(model, self.inputs(self.pool[i % 2]), stream=ln,
-                                                   static_input=self.inputs(self.pool[i % 2])) for i, ln in enumerate(lanes)]
+                                                   static_input=self.inputs(self.pool[i % 2]),
+                                                   sampling_mode=self.sampling_mode) for i, ln in enumerate(lanes)]
                 except Exception as ex:      # capture unavailable (e.g. under a profiler): same kernels, enqueued from Python
                     self.graphs, args.no_graphs = None, True
                     print("bench: CUDA-graph capture failed (%s); eager launches" % repr(ex)[:120], file=sys.stderr)
@@ -806,6 +819,7 @@ def sub_config(args, which, rank, local_rank, world, K):
         par = None if args.no_parity else r.gate()
         recs.append({"config": which, "workload": cfg["what"], "scenes_per_gpu": cfg["batch"], "points": cfg["points"],
                      "precision": cfg["precision"], "batches_in_flight": cfg["lanes"], "steps": K,
+                     "sampling_mode": getattr(r, "sampling_mode", "latency"),
                      "value": world * cfg["batch"] * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,
                      "gpu_launches_per_step": launches / K, "parity": par})
         del r
@@ -897,7 +911,7 @@ def run_ours(args, rank, local_rank, world):
     with torch.no_grad():
         if rank == 0:
             if not args.no_kernel_breakdown:
-                rows = kernel_breakdown(net, run.pool[0], precision, pk)
+                rows = kernel_breakdown(net, run.pool[0], precision, pk, sampling_mode=getattr(run, "sampling_mode", "latency"))
             try:
                 ref_cuda = None if args.no_reference_cuda else reference_cuda_arm(run.pool[0], run.sd_cpu, run.out0,
                                                                                   lanes=cfg["lanes"])
@@ -920,6 +934,7 @@ def run_ours(args, rank, local_rank, world):
                                       % (sample.shape[0], B, cores)}
     run.barrier()
     lanes_n = len(run.lanes)
+    sampling_mode_used = getattr(run, "sampling_mode", "latency")
     del run
     torch.cuda.empty_cache()
 
@@ -942,6 +957,7 @@ def run_ours(args, rank, local_rank, world):
                            "scenes_per_gpu": B, "points": cfg["points"], "feature_channels": 129,
                            "precision": precision, "sharding": "by scene, no collective",
                            "batches_in_flight": lanes_n, "cuda_graphs": not args.no_graphs,
+                           "sampling_mode": sampling_mode_used,
                            "sm_partition": {"fps": part.sms[0], "main": part.sms[1]} if part else None,
                            "l2": "each input batch is %.0f MB (> 126 MB L2); two batches alternate" % (in_bytes / 1e6)},
                 "gpu_launches": launches * world, "gpu_launches_per_step": launches / K,
@@ -958,13 +974,13 @@ def run_ours(args, rank, local_rank, world):
             traffic = ncu_traffic()
             line["roofline"] = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"],
                                 "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
-                                "traffic": traffic.get(dom["kernel"]),
+                                "traffic": traffic.get(dom["kernel"] + (":bucketed" if dom.get("variant", "").startswith("bucketed") else "")),
                                 "share_of_step": dom["share"], "us_per_launch": dom["us"],
                                 "dominance": "largest share of SM-time of a step (launch duration x fraction of the SMs the "
                                              "launch can occupy: the sampling launches run 1-8 CTAs per scene, everything else is "
                                              "counted as the whole GPU); share_serial in roofline_kernels is plain duration",
                                 "peak_source": pk["source"] + (" burst" if dom["bound"] == "tensor" else "")}
-            for extra in ("rounds_per_s", "sm_share"):
+            for extra in ("rounds_per_s", "sm_share", "variant"):
                 if extra in dom:
                     line["roofline"][extra] = dom[extra]
             if "rounds_per_s" in dom:
@@ -978,12 +994,13 @@ def run_ours(args, rank, local_rank, world):
                                          "note": "algorithmic FLOPs / bytes per scene x scenes/s per GPU"}
             line["roofline_kernels"] = [
                 {k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()
-                 if k in ("kernel", "bound", "us", "share", "share_serial", "achieved", "unit", "frac", "hbm_gbs",
+                 if k in ("kernel", "variant", "bound", "us", "share", "share_serial", "achieved", "unit", "frac", "hbm_gbs",
                           "rounds_per_s", "sm_share", "layer_tflops")}
                 for r in rows]
             for r in line["roofline_kernels"]:
-                if r["kernel"] in traffic:
-                    r["traffic"] = traffic[r["kernel"]]
+                key = r["kernel"] + (":bucketed" if r.get("variant", "").startswith("bucketed") else "")
+                if key in traffic:
+                    r["traffic"] = traffic[key]
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         if ref_cuda:

@@ -141,11 +141,16 @@ int pn2_furthest_point_sampling_xyz(int b, int n, int m, const float *xyz, int *
 int pn2_furthest_point_sampling_rows(int b, int n, int m, const float *rows, int pitch, int *idxs,
                                      float *new_xyz, float *xyz_copy, pn2_stream_t stream);
 
-/* Same two entry points with a workspace of pn2_furthest_point_sampling_workspace_bytes(b, n, m) bytes (16-byte
- * aligned device memory, no initialisation needed).  Scenes of more than 8192 points then run the bucketed kernel
- * (csrc/fps_bucket.cu: one CTA per scene, points binned into spatial buckets, the distance update pruned exactly
- * by bounding boxes); without a workspace, or for small scenes, the register-resident kernels of csrc/fps.cu run.
- * Results are identical either way. */
+/* Same two entry points with a workspace of pn2_furthest_point_sampling_workspace_bytes[_mode](b, n, m) bytes (16-byte
+ * aligned device memory, no initialisation needed).  With a workspace the bucketed kernel runs (csrc/fps_bucket.cu: one
+ * CTA per scene, points binned into spatial buckets, the distance update pruned exactly by bounding boxes); without
+ * one (the size query returned 0) the register-resident kernels of csrc/fps.cu run.  Results are identical either
+ * way; the two differ in what they optimise.  PN2_FPS_LATENCY (what the plain size query answers for): the fastest
+ * single launch -- the cluster kernel up to 81 920 points.  PN2_FPS_THROUGHPUT: the least SM time per scene, for callers
+ * that keep enough batches in flight to fill the GPU (>= ~150 scenes) -- the bucketed kernel from 32 768 points. */
+#define PN2_FPS_LATENCY 0
+#define PN2_FPS_THROUGHPUT 1
+size_t pn2_furthest_point_sampling_workspace_bytes_mode(int b, int n, int m, int mode);
 int pn2_furthest_point_sampling_xyz_ws(int b, int n, int m, const float *xyz, int *idxs, float *new_xyz,
                                        void *workspace, size_t workspace_bytes, pn2_stream_t stream);
 int pn2_furthest_point_sampling_rows_ws(int b, int n, int m, const float *rows, int pitch, int *idxs,

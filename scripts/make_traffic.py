@@ -37,6 +37,27 @@ for r in data:
                   "%.2f" % (rd / 1e6), "%.2f" % (wr / 1e6), g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                   g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"), g("launch__registers_per_thread"),
                   g("launch__grid_size"), g("launch__block_size"), g("smsp__issue_active.avg.pct_of_peak_sustained_active")))
+# the throughput-mode sampling kernel of the same level (fused.sampling_mode("throughput"): csrc/fps_bucket.cu at 40 000
+# points, 8 scenes) from its own capture, scripts/gpu_r2_final.sh -> gpurun_out/prof_fpsb40k_r2.ncu-rep
+import os
+extra_rep = sys.argv[3] if len(sys.argv) > 3 else "gpurun_out/prof_fpsb40k_r2.ncu-rep"
+try:
+    prev = json.load(open("profiles/ncu_traffic.json"))
+except Exception:
+    prev = {}
+if os.path.exists(extra_rep):
+    o2 = subprocess.run(["ncu", "-i", extra_rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    r2 = list(csv.reader(io.StringIO(o2)))
+    h2, u2, d2 = r2[0], r2[1], r2[2:]
+    c2 = {h: i for i, h in enumerate(h2)}
+    for r in d2:
+        if "fps_bucket_kernel" in r[c2["Kernel Name"]]:
+            tot = 0.0
+            for nm in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[c2[nm]]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u2[c2[nm]]]
+            traffic["fps_sa1:bucketed"] = int(tot)
+elif "fps_sa1:bucketed" in prev:
+    traffic["fps_sa1:bucketed"] = prev["fps_sa1:bucketed"]
 json.dump(traffic, open("profiles/ncu_traffic.json", "w"), indent=1, sort_keys=True)
 with open(out_md, "w") as f:
     f.write("# One bench step (B=8, 40k points, bf16 arm, lanes=1) under `ncu --set full --clock-control none`\n\n"

@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "pn2_ball_query": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, _p]),
     "pn2_ball_query_workspace_bytes": (c_size_t, [_i, _i, _i, _i]),
     "pn2_ball_query_ws": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, _p, c_size_t, _p]),
+    "pn2_furthest_point_sampling_workspace_bytes_mode": (c_size_t, [_i, _i, _i, _i]),
     "pn2_ball_query_grid_build": (_i, [_i, _i, _i, _f, _i, _p, _i, _p, c_size_t, _p]),
     "pn2_ball_query_grid_query": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, c_size_t, _p]),
     "pn2_group_rows": (_i, [_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _i, _p, _p]),

@@ -34,8 +34,8 @@
 namespace pn2 {
 
 // fps_bucket.cu: one CTA per scene over spatially bucketed points (large scenes, needs a workspace)
-int fps_bucket_min_points();
-size_t fps_bucket_workspace_bytes(int b, int n);
+int fps_bucket_min_points(int mode);
+size_t fps_bucket_workspace_bytes(int b, int n, int mode);
 int fps_bucket_launch(int b, int n, int m, int lg_bs, int cnt, const float *xyz, int pitch, int *idxs, float *new_xyz,
                       float *xyz_copy, void *ws, size_t ws_bytes, long long *prof, cudaStream_t stream);
 
@@ -552,7 +552,13 @@ using namespace pn2;
 
 extern "C" size_t pn2_furthest_point_sampling_workspace_bytes(int b, int n, int)
 {
-    return b > 0 ? fps_bucket_workspace_bytes(b, n) : 0;
+    return b > 0 ? fps_bucket_workspace_bytes(b, n, PN2_FPS_LATENCY) : 0;
+}
+
+extern "C" size_t pn2_furthest_point_sampling_workspace_bytes_mode(int b, int n, int, int mode)
+{
+    if (mode != PN2_FPS_LATENCY && mode != PN2_FPS_THROUGHPUT) return 0;
+    return b > 0 ? fps_bucket_workspace_bytes(b, n, mode) : 0;
 }
 
 static int fps_entry(int b, int n, int m, const float *xyz, int pitch, int *idxs, float *new_xyz, float *xyz_copy,
@@ -570,7 +576,8 @@ static int fps_entry(int b, int n, int m, const float *xyz, int pitch, int *idxs
     }
     if (!xyz) return PN2_ERR_INVALID_ARGUMENT;
     // large scenes with a workspace: spatially bucketed points, one CTA per scene (fps_bucket.cu)
-    const size_t need = fps_bucket_workspace_bytes(b, n);
+    // The caller chooses by handing over a workspace: the size query of its mode returned non-zero
+    const size_t need = fps_bucket_workspace_bytes(b, n, PN2_FPS_THROUGHPUT);
     if (ws && need && ws_bytes >= need) {
         const int lg = ref_block_lg(n), bs = 1 << lg;
         return fps_bucket_launch(b, n, m, lg, (n + bs - 1) / bs, xyz, pitch, idxs, new_xyz, xyz_copy, ws, ws_bytes, prof,

@@ -115,8 +115,13 @@ __device__ __forceinline__ Cand warp_best(const Cand &c, int lg_bs, int cnt)
 // PPL points per lane in a bucket (bucket = 32*PPL points), CH buckets per super-bucket, SS super-buckets per
 // thread; SDIST: running distances in shared memory (else in the workspace).  The CTA starts with kBT threads for the
 // binning; the rounds run on the first `nwa` warps only (one thread per super-bucket), the others leave.
-template <int PPL, int CH, int SS, bool SDIST>
-__global__ void __launch_bounds__(kBT, 1)
+// PHASE 0: the whole kernel.  PHASE 1 / 2: the same code as two launches -- the binning (kBT threads, 128 KB histogram)
+// and the rounds (only the `nwa` warps that run them, no histogram: <= kSplitThreads threads at <= 102 registers and
+// ~30 KB of shared memory, so that TWO scenes share an SM; the rounds are barrier- and latency-bound, issue slots a
+// third busy).  The count of competing points travels through the workspace.
+constexpr int kSplitThreads = 320;
+template <int PPL, int CH, int SS, bool SDIST, int PHASE = 0>
+__global__ void __launch_bounds__(PHASE == 2 ? kSplitThreads : kBT, PHASE == 2 ? 2 : 1)
 fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int pitch, int *__restrict__ idxs,
                   float *__restrict__ new_xyz, float *__restrict__ xyz_copy, unsigned char *__restrict__ ws,
                   size_t ws_stride, int npad, int nwa, long long *__restrict__ prof)
@@ -148,6 +153,9 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     float4 *meta4 = reinterpret_cast<float4 *>(mbase);
     uint32_t *cidx = reinterpret_cast<uint32_t *>(mbase + (size_t)16 * nbcap);
 
+    int *nv_slot = reinterpret_cast<int *>(w + (((size_t)20 * npad + (size_t)2 * n + 3) & ~(size_t)3));
+    int nv = 0;                                          // points that compete (not skipped)
+    if constexpr (PHASE != 2) {
     for (int i = tid; i < kCells; i += kBT) hist[i] = 0u;
 
     // ---- P1: bounding box of the competing, finite points (+ the contiguous xyz copy) -----------------------
@@ -237,7 +245,7 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
         if (lane == kBW - 1) wbase[kBW] = inc;
     }
     __syncthreads();
-    const int nv = (int)wbase[kBW];                      // points that compete (not skipped)
+    nv = (int)wbase[kBW];
 
     // ---- P4: counting sort into the workspace ---------------------------------------------------------------
 #pragma unroll 4
@@ -249,6 +257,13 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
         }
     }
     __syncthreads();                                     // histogram dead from here: `dist` / the bucket records may alias it
+    if constexpr (PHASE == 1) {
+        if (tid == 0) *nv_slot = nv;
+        return;
+    }
+    } else {
+        nv = *nv_slot;                                   // written by the PHASE 1 launch that precedes this one on the stream
+    }
     const int NW = nwa;                                  // warps that run the rounds
     if (warp >= NW) return;
     const int nthr = NW * 32;
@@ -614,9 +629,27 @@ bool choose(int n, BucketCfg *c)
     const size_t h = (size_t)kCells * 4, need = (c->sdist ? (size_t)c->npad * 4 : 0) + meta;
     if (need > kMaxSmem) return false;
     c->smem = need > h ? need : h;
-    const size_t bytes = (size_t)20 * c->npad + (size_t)2 * n;
+    const size_t bytes = (size_t)20 * c->npad + (size_t)2 * n + 8;      // + the count of competing points (split launch)
     c->stride = (bytes + 255) / 256 * 256;
     return true;
+}
+
+// Two launches (binning, then the rounds on nwa warps with two scenes per SM): scenes of up to 40 960 points, whose
+// rounds need <= kSplitThreads threads; distances live in the workspace (L2).  Opt-in: PN2_FPS_BUCKET_SPLIT=1.
+int launch_split(const BucketCfg &c, int b, int n, int m, int lg_bs, int cnt, const float *xyz, int pitch, int *idxs,
+                 float *new_xyz, float *xyz_copy, void *ws, long long *prof, cudaStream_t stream)
+{
+    auto ka = fps_bucket_kernel<1, kCH, 1, false, 1>;
+    auto kb = fps_bucket_kernel<1, kCH, 1, false, 2>;
+    const size_t hist = (size_t)kCells * 4, meta = (size_t)20 * (c.npad / 32);
+    PN2_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist));
+    PN2_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta));
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    ka<<<b, kBT, hist, stream>>>(n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, w, c.stride, c.npad, c.nwa, prof);
+    kb<<<b, c.nwa * 32, meta, stream>>>(n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, w, c.stride, c.npad, c.nwa, prof);
+    count_launches(1);
+    PN2_LAUNCH_CHECK("fps_bucket_kernel(split)");
+    return PN2_OK;
 }
 
 template <int PPL, int SS, bool SDIST>
@@ -633,22 +666,25 @@ int launch_cfg(const BucketCfg &c, int b, int n, int m, int lg_bs, int cnt, cons
 
 }  // namespace
 
-// smallest scene the bucketed kernel is used for (below, the register-resident kernels of fps.cu win)
-int fps_bucket_min_points()
+// Smallest scene the bucketed kernel is used for, by the caller's objective (PN2_FPS_LATENCY / PN2_FPS_THROUGHPUT).
+// Measured on B200 (B = 8, scripts/fps_bucket_bench.py, scripts/gpu_r2_check9.sh):
+//   * one launch: at 40 000 points the register-resident cluster kernel is faster (1.36 ms against 4.1 ms: a round here
+//     is a chain of ~430 dependent warp instructions); at 200 000 points this kernel is (12.3 ms against 15.6 ms);
+//   * SM time, which is what bounds a caller with many batches in flight: this kernel holds ONE SM per scene, 4.1 SM-ms
+//     at 40 000 points, the cluster kernel 8 CTAs at three per SM for 2.1 ms = 5.7 SM-ms.  With >= 19 eight-scene
+//     batches in flight (148 scenes) the bench step runs at 14.2-15.2 k scenes/s on this kernel against 13.1 k.
+// Latency mode: beyond what the cluster kernel covers with 8 CTAs.  Throughput mode: from 32 768 points.
+int fps_bucket_min_points(int mode)
 {
-    // Measured on B200 (scripts/fps_bucket_bench.py, B = 8): at 40 000 points the register-resident cluster kernel is
-    // the faster launch (1.36 ms against 4.1 ms: a round here is a chain of ~430 dependent warp instructions); at
-    // 200 000 points this kernel is (12.3 ms against 15.6 ms) and needs one SM per scene instead of sixteen half-SMs
-    // (1.76 ms against 9.0 ms per 8-scene batch with several batches in flight).  Default: beyond what the cluster
-    // kernel covers with 8 CTAs.
     const char *e = getenv("PN2_FPS_BUCKET_MIN");    // tests / sweeps: 1 = always, a huge value = never
-    return e ? atoi(e) : 81921;
+    if (e) return atoi(e);
+    return mode == PN2_FPS_THROUGHPUT ? 32768 : 81921;
 }
 
-size_t fps_bucket_workspace_bytes(int b, int n)
+size_t fps_bucket_workspace_bytes(int b, int n, int mode)
 {
     BucketCfg c;
-    if (n < fps_bucket_min_points() || !choose(n, &c)) return 0;
+    if (n < fps_bucket_min_points(mode) || !choose(n, &c)) return 0;
     return c.stride * (size_t)b;
 }
 
@@ -660,6 +696,12 @@ int fps_bucket_launch(int b, int n, int m, int lg_bs, int cnt, const float *xyz,
     if (!ws || ws_bytes < c.stride * (size_t)b || (reinterpret_cast<uintptr_t>(ws) & 15)) return PN2_ERR_WORKSPACE;
 #define PN2_FPSB_GO(PPL, SS, SD) \
     return launch_cfg<PPL, SS, SD>(c, b, n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, ws, prof, stream)
+    // Measured on the 20-lane bench step at the driver's 20 steps: 15.1-15.4 k scenes/s as one launch, 14.0 k split
+    // (the 512-thread binning CTAs cannot share an SM with two rounds CTAs and queue behind them); 16.6 k against
+    // 15.2 k for the split form in a long run with 32 lanes.  Off by default.
+    static const bool split = [] { const char *e = getenv("PN2_FPS_BUCKET_SPLIT"); return e && atoi(e) != 0; }();
+    if (split && c.ppl == 1 && c.nwa * 32 <= kSplitThreads)
+        return launch_split(c, b, n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, ws, prof, stream);
     if (c.ppl == 1) { if (c.sdist) PN2_FPSB_GO(1, 1, true); else PN2_FPSB_GO(1, 1, false); }
     if (c.ppl == 2) PN2_FPSB_GO(2, 1, false);
     if (c.ss == 1) PN2_FPSB_GO(4, 1, false);

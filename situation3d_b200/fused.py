@@ -6,6 +6,8 @@ hands them to the C ABI's pack functions and launches the fused kernels on the c
 """
 import ctypes
 
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -198,10 +200,29 @@ def rows_from_channels(features):
     return rows
 
 
+_SAMPLING_MODE = [0]          # PN2_FPS_LATENCY; see sampling_mode()
+
+
+@contextlib.contextmanager
+def sampling_mode(mode):
+    """``with fused.sampling_mode("throughput"):`` -- sampling launches issued inside (and graphs captured inside) choose
+    the kernel with the least SM time per scene instead of the fastest single launch (include/pn2_b200.h:
+    PN2_FPS_THROUGHPUT; at 40 000 points the bucketed one-CTA-per-scene kernel instead of the 8-CTA cluster kernel).
+    For callers that keep >= ~150 scenes in flight (graphs.BackbonePipeline decides by lanes x batch).  Results are
+    identical in both modes."""
+    value = {"latency": 0, "throughput": 1}[mode]
+    prev = _SAMPLING_MODE[0]
+    _SAMPLING_MODE[0] = value
+    try:
+        yield
+    finally:
+        _SAMPLING_MODE[0] = prev
+
+
 def _fps_workspace(B, N, npoint, device):
-    """Scratch of the bucketed sampling kernel (csrc/fps_bucket.cu), from PyTorch's caching allocator; None for
-    small scenes (register-resident kernels)."""
-    nbytes = lib.pn2_furthest_point_sampling_workspace_bytes(B, N, npoint)
+    """Scratch of the bucketed sampling kernel (csrc/fps_bucket.cu), from PyTorch's caching allocator; None when the
+    register-resident kernels run (small scenes; mid-sized scenes in latency mode)."""
+    nbytes = lib.pn2_furthest_point_sampling_workspace_bytes_mode(B, N, npoint, _SAMPLING_MODE[0])
     return (torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes) if nbytes else (None, 0)
 
 

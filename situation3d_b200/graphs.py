@@ -28,8 +28,16 @@ def _as_inputs(example):
     return {"point_clouds": example}
 
 
+def pick_sampling_mode(scenes_in_flight):
+    """"throughput" once the caller keeps enough scenes in flight to fill the GPU with one sampling CTA per scene
+    (fused.sampling_mode, include/pn2_b200.h PN2_FPS_THROUGHPUT), "latency" otherwise."""
+    return "throughput" if scenes_in_flight >= 128 else "latency"
+
+
 class GraphedBackbone:
-    def __init__(self, net, example, stream=None, static_input=None, warmup=2):
+    def __init__(self, net, example, stream=None, static_input=None, warmup=2, sampling_mode="latency"):
+        """``sampling_mode``: which FPS kernel the captured step uses for mid-sized scenes (results are identical):
+        "latency" = fastest single step, "throughput" = least SM time, for many steps in flight (pick_sampling_mode)."""
         assert not net.training, "the fused (forward-only) path is what gets captured"
         self.net = net
         example = _as_inputs(example)
@@ -37,7 +45,8 @@ class GraphedBackbone:
         self.stream = stream if stream is not None else lane_stream(first.device)
         self.static_in = _as_inputs(static_input) if static_input is not None else {k: torch.empty_like(v) for k, v in example.items()}
         from ._lib import lib
-        with torch.no_grad():
+        from . import fused
+        with torch.no_grad(), fused.sampling_mode(sampling_mode):
             with torch.cuda.stream(self.stream):
                 if static_input is None:
                     for k, v in example.items():
@@ -80,14 +89,21 @@ class BackbonePipeline:
     are in flight and a ticket's host buffers stay valid until ``lanes`` further submissions.
     """
 
-    def __init__(self, net, example, lanes=8, outputs=("fp2_features", "fp2_xyz", "fp2_inds"), streams=None):
+    def __init__(self, net, example, lanes=8, outputs=("fp2_features", "fp2_xyz", "fp2_inds"), streams=None,
+                 sampling_mode=None):
         example = _as_inputs(example)
         first = next(iter(example.values()))
         dev = first.device if first.is_cuda else torch.device("cuda", torch.cuda.current_device())
         example = {k: v.to(dev) for k, v in example.items()}
         self.streams = list(streams) if streams is not None else [lane_stream(dev) for _ in range(lanes)]
         self.inputs = [{k: v.clone() for k, v in example.items()} for _ in self.streams]
-        self.steps = [GraphedBackbone(net, example, stream=st, static_input=buf) for st, buf in zip(self.streams, self.inputs)]
+        # From host buffers the step is bound by the PCIe copy, not by SM time: the fastest single step ("latency") keeps
+        # the lanes short; measured 4.6 k scenes/s end to end against 3.5 k with the throughput-mode sampling kernel.
+        if sampling_mode is None:
+            sampling_mode = "latency"
+        self.sampling_mode = sampling_mode
+        self.steps = [GraphedBackbone(net, example, stream=st, static_input=buf, sampling_mode=sampling_mode)
+                      for st, buf in zip(self.streams, self.inputs)]
         self.outputs = tuple(outputs)
         self.host = [{k: torch.empty_like(s.out[k], device="cpu").pin_memory() for k in self.outputs} for s in self.steps]
         self.done = [torch.cuda.Event() for _ in self.streams]

@@ -45,6 +45,11 @@ def test_library_basics_without_gpu():
     assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 200000, 4096) == 8 * ((20 * 200064 + 2 * 200000 + 255) // 256 * 256)
     assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 40000, 2048) == 0   # register-resident cluster kernel
     assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 2048, 1024) == 0
+    # PN2_FPS_THROUGHPUT (1): the bucketed kernel already from 32 768 points; PN2_FPS_LATENCY (0) = the plain query
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes_mode(8, 40000, 2048, 0) == 0
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes_mode(8, 40000, 2048, 1) > 0
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes_mode(8, 20000, 2048, 1) == 0
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes_mode(8, 40000, 2048, 7) == 0
     # argument validation happens before any CUDA call
     assert _lib.lib.pn2_gather_points(-1, 1, 1, 1, None, None, None, None) == -1
     assert _lib.lib.pn2_ball_query(1, 10, 4, 0.5, 8, None, None, None, None) == -1

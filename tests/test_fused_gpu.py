@@ -583,6 +583,32 @@ def test_group_rows_kernel_matches_query_and_group_on_rows():
                 torch.testing.assert_close(ra.grad, rb.grad, rtol=1e-5, atol=1e-5)
 
 
+def test_sampling_modes_give_identical_results():
+    """fused.sampling_mode("throughput") swaps the FPS kernel of 40 000-point scenes (bucketed one-CTA-per-scene kernel
+    instead of the 8-CTA cluster kernel); every output of the backbone stays bit-identical, eagerly and in a captured step."""
+    from situation3d_b200 import fused
+    from situation3d_b200.backbone_module import Pointnet2Backbone
+    from situation3d_b200.graphs import GraphedBackbone, pick_sampling_mode
+    from situation3d_b200.synthetic import make_batch, randomize_bn_stats
+    from situation3d_b200._lib import lib
+    assert lib.pn2_furthest_point_sampling_workspace_bytes_mode(2, 40000, 2048, 0) == 0
+    assert lib.pn2_furthest_point_sampling_workspace_bytes_mode(2, 40000, 2048, 1) > 0
+    assert pick_sampling_mode(8) == "latency" and pick_sampling_mode(160) == "throughput"
+    torch.manual_seed(0)
+    net = randomize_bn_stats(Pointnet2Backbone(input_feature_dim=9, precision="bf16")).eval().cuda()
+    pc = torch.from_numpy(make_batch(2, 40000, 9)).cuda()
+    with torch.no_grad():
+        a = net({"point_clouds": pc})
+        with fused.sampling_mode("throughput"):
+            b = net({"point_clouds": pc})
+        g = GraphedBackbone(net, pc, sampling_mode="throughput")
+        c = g(pc)
+        torch.cuda.synchronize()
+    for k in ("sa1_inds", "sa2_inds", "sa3_inds", "sa4_inds", "fp2_inds", "sa1_xyz", "fp2_xyz", "fp2_features"):
+        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a[k], c[k]), k
+
+
 def test_compact_input_is_bit_identical():
     """fp32 coordinates + bf16 feature rows (Pointnet2Backbone.pack_point_clouds: half the host-to-device bytes) give
     bit-identical results to the reference's fp32 point_clouds on the bf16 arm, eagerly and through the pipeline from
