@@ -119,9 +119,11 @@ __device__ __forceinline__ Cand warp_best(const Cand &c, int lg_bs, int cnt)
 // and the rounds (only the `nwa` warps that run them, no histogram: <= kSplitThreads threads at <= 102 registers and
 // ~30 KB of shared memory, so that TWO scenes share an SM; the rounds are barrier- and latency-bound, issue slots a
 // third busy).  The count of competing points travels through the workspace.
+// PHASE 3: one launch again, but of kSplitThreads threads from the start and with the histogram in the workspace (L2
+// atomics instead of shared memory): the binning is slower, the whole kernel fits two scenes per SM.
 constexpr int kSplitThreads = 320;
 template <int PPL, int CH, int SS, bool SDIST, int PHASE = 0>
-__global__ void __launch_bounds__(PHASE == 2 ? kSplitThreads : kBT, PHASE == 2 ? 2 : 1)
+__global__ void __launch_bounds__(PHASE >= 2 ? kSplitThreads : kBT, PHASE >= 2 ? 2 : 1)
 fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xyz, int pitch, int *__restrict__ idxs,
                   float *__restrict__ new_xyz, float *__restrict__ xyz_copy, unsigned char *__restrict__ ws,
                   size_t ws_stride, int npad, int nwa, long long *__restrict__ prof)
@@ -130,7 +132,7 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     constexpr int BS = 32 * PPL;
     constexpr int kWords = SS * CH;                          // bitmap words per warp: one per (ss, c), bit = owner lane
     extern __shared__ __align__(16) unsigned char dyn[];
-    uint32_t *hist = reinterpret_cast<uint32_t *>(dyn);     // prologue: cell histogram / offsets
+    uint32_t *hist = reinterpret_cast<uint32_t *>(dyn);     // prologue: cell histogram / offsets (PHASE 3: in the workspace)
     __shared__ uint32_t red[kBW][8];
     __shared__ uint32_t wbase[kBW + 1];
     __shared__ __align__(8) int2 tableA[kBW];                // per warp: best (distance bits, bucket) it accounts for this round
@@ -153,16 +155,22 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     float4 *meta4 = reinterpret_cast<float4 *>(mbase);
     uint32_t *cidx = reinterpret_cast<uint32_t *>(mbase + (size_t)16 * nbcap);
 
-    int *nv_slot = reinterpret_cast<int *>(w + (((size_t)20 * npad + (size_t)2 * n + 3) & ~(size_t)3));
+    const size_t nv_off = ((size_t)20 * npad + (size_t)2 * n + 3) & ~(size_t)3;
+    int *nv_slot = reinterpret_cast<int *>(w + nv_off);
     int nv = 0;                                          // points that compete (not skipped)
+    constexpr int NT = PHASE == 3 ? kSplitThreads : kBT;  // threads of the binning
+    constexpr int NWB = NT / 32;                          // ... its warps
+    constexpr int SW = PHASE == 3 ? 8 : kBW;              // warps that scan the histogram (the cells divide evenly)
+    constexpr int CPW = kCells / SW;
+    if constexpr (PHASE == 3) hist = reinterpret_cast<uint32_t *>(w + ((nv_off + 4 + 15) & ~(size_t)15));
     if constexpr (PHASE != 2) {
-    for (int i = tid; i < kCells; i += kBT) hist[i] = 0u;
+    for (int i = tid; i < kCells; i += NT) hist[i] = 0u;
 
     // ---- P1: bounding box of the competing, finite points (+ the contiguous xyz copy) -----------------------
     const bool vec4 = (pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 4
-    for (int k = tid; k < n; k += kBT) {
+    for (int k = tid; k < n; k += NT) {
         float x, y, z;
         if (vec4) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(p + (size_t)pitch * k));
@@ -188,8 +196,8 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     float lo3[3], ext = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const uint32_t lo = __reduce_min_sync(kFullMask, lane < kBW ? red[lane][a] : 0xffffffffu);
-        const uint32_t hi = __reduce_max_sync(kFullMask, lane < kBW ? red[lane][3 + a] : 0u);
+        const uint32_t lo = __reduce_min_sync(kFullMask, lane < NWB ? red[lane][a] : 0xffffffffu);
+        const uint32_t hi = __reduce_max_sync(kFullMask, lane < NWB ? red[lane][3 + a] : 0u);
         lo3[a] = ord_inv(lo);
         ext = fmaxf(ext, ord_inv(hi) - lo3[a]);          // -inf when there is no finite point
     }
@@ -201,7 +209,7 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     const int sp = cp ? 3 : pitch;
     constexpr float kQMax = (float)((1 << kCellBits) - 1);
 #pragma unroll 4
-    for (int k = tid; k < n; k += kBT) {
+    for (int k = tid; k < n; k += NT) {
         const float x = src[(size_t)sp * k], y = src[(size_t)sp * k + 1], z = src[(size_t)sp * k + 2];
         uint32_t c = kSkipCell;
         if (!((double)sqnorm3(x, y, z) <= 1e-3)) {
@@ -216,10 +224,10 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     __syncthreads();
 
     // ---- P3: exclusive scan of the histogram (each warp scans its 2048 cells; warp bases added on use) ------
-    {
+    if (warp < SW) {
         uint32_t carry = 0;
-        const int c0 = warp * kCellsPerWarp;
-        for (int i = 0; i < kCellsPerWarp; i += 32) {
+        const int c0 = warp * CPW;
+        for (int i = 0; i < CPW; i += 32) {
             const uint32_t v = hist[c0 + i + lane];
             uint32_t inc = v;
 #pragma unroll
@@ -234,25 +242,25 @@ fps_bucket_kernel(int n, int m, int lg_bs, int cnt, const float *__restrict__ xy
     }
     __syncthreads();
     if (warp == 0) {
-        const uint32_t v = lane < kBW ? red[lane][6] : 0u;
+        const uint32_t v = lane < SW ? red[lane][6] : 0u;
         uint32_t inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(kFullMask, inc, d);
             if (lane >= d) inc += t;
         }
-        if (lane < kBW) wbase[lane] = inc - v;
-        if (lane == kBW - 1) wbase[kBW] = inc;
+        if (lane < SW) wbase[lane] = inc - v;
+        if (lane == SW - 1) wbase[SW] = inc;
     }
     __syncthreads();
-    nv = (int)wbase[kBW];
+    nv = (int)wbase[SW];
 
     // ---- P4: counting sort into the workspace ---------------------------------------------------------------
 #pragma unroll 4
-    for (int k = tid; k < n; k += kBT) {
+    for (int k = tid; k < n; k += NT) {
         const uint32_t c = cellid[k];
         if (c != kSkipCell) {
-            const uint32_t pos = atomicAdd(&hist[c], 1u) + wbase[c / kCellsPerWarp];
+            const uint32_t pos = atomicAdd(&hist[c], 1u) + wbase[c / CPW];
             pts[pos] = make_float4(src[(size_t)sp * k], src[(size_t)sp * k + 1], src[(size_t)sp * k + 2], __int_as_float(k));
         }
     }
@@ -629,7 +637,8 @@ bool choose(int n, BucketCfg *c)
     const size_t h = (size_t)kCells * 4, need = (c->sdist ? (size_t)c->npad * 4 : 0) + meta;
     if (need > kMaxSmem) return false;
     c->smem = need > h ? need : h;
-    const size_t bytes = (size_t)20 * c->npad + (size_t)2 * n + 8;      // + the count of competing points (split launch)
+    // + the count of competing points (split launch) + the histogram of the two-scenes-per-SM variant
+    const size_t bytes = (size_t)20 * c->npad + (size_t)2 * n + 32 + (size_t)kCells * 4;
     c->stride = (bytes + 255) / 256 * 256;
     return true;
 }
@@ -649,6 +658,22 @@ int launch_split(const BucketCfg &c, int b, int n, int m, int lg_bs, int cnt, co
     kb<<<b, c.nwa * 32, meta, stream>>>(n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, w, c.stride, c.npad, c.nwa, prof);
     count_launches(1);
     PN2_LAUNCH_CHECK("fps_bucket_kernel(split)");
+    return PN2_OK;
+}
+
+// One launch of kSplitThreads threads, histogram in the workspace: two scenes per SM (PN2_FPS_BUCKET_SPLIT=2).
+// Measured at 40 000 points (scripts/gpu_r2_check10.sh): 5.2 ms alone against 4.1 ms; with 296 scenes in one launch
+// 0.193 ms of the GPU per 8 scenes against 0.230 ms -- but the pipelined bench step, where these CTAs share the SMs with
+// the other kernels of 20-40 batches, runs at 13.7 k scenes/s against 15.4 k.  Off by default.
+int launch_compact(const BucketCfg &c, int b, int n, int m, int lg_bs, int cnt, const float *xyz, int pitch, int *idxs,
+                   float *new_xyz, float *xyz_copy, void *ws, long long *prof, cudaStream_t stream)
+{
+    auto kern = fps_bucket_kernel<1, kCH, 1, false, 3>;
+    const size_t meta = (size_t)20 * (c.npad / 32);
+    PN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)meta));
+    kern<<<b, kSplitThreads, meta, stream>>>(n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy,
+                                             static_cast<unsigned char *>(ws), c.stride, c.npad, c.nwa, prof);
+    PN2_LAUNCH_CHECK("fps_bucket_kernel(compact)");
     return PN2_OK;
 }
 
@@ -699,8 +724,10 @@ int fps_bucket_launch(int b, int n, int m, int lg_bs, int cnt, const float *xyz,
     // Measured on the 20-lane bench step at the driver's 20 steps: 15.1-15.4 k scenes/s as one launch, 14.0 k split
     // (the 512-thread binning CTAs cannot share an SM with two rounds CTAs and queue behind them); 16.6 k against
     // 15.2 k for the split form in a long run with 32 lanes.  Off by default.
-    static const bool split = [] { const char *e = getenv("PN2_FPS_BUCKET_SPLIT"); return e && atoi(e) != 0; }();
-    if (split && c.ppl == 1 && c.nwa * 32 <= kSplitThreads)
+    static const int split = [] { const char *e = getenv("PN2_FPS_BUCKET_SPLIT"); return e ? atoi(e) : 0; }();
+    if (split == 2 && c.ppl == 1 && c.nwa * 32 <= kSplitThreads)
+        return launch_compact(c, b, n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, ws, prof, stream);
+    if (split == 1 && c.ppl == 1 && c.nwa * 32 <= kSplitThreads)
         return launch_split(c, b, n, m, lg_bs, cnt, xyz, pitch, idxs, new_xyz, xyz_copy, ws, prof, stream);
     if (c.ppl == 1) { if (c.sdist) PN2_FPSB_GO(1, 1, true); else PN2_FPSB_GO(1, 1, false); }
     if (c.ppl == 2) PN2_FPSB_GO(2, 1, false);

@@ -42,7 +42,7 @@ def test_library_basics_without_gpu():
     # large scenes: the bucketed kernel's scratch, per scene 20 bytes per (padded) point + 2 per point, 256-byte aligned
     # large scenes: the bucketed kernel's scratch, per scene 20 bytes per point (padded to whole 128-point buckets) + 2
     # per point, 256-byte aligned
-    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 200000, 4096) == 8 * ((20 * 200064 + 2 * 200000 + 255) // 256 * 256)
+    assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 200000, 4096) == 8 * ((20 * 200064 + 2 * 200000 + 32 + 4 * 32768 + 255) // 256 * 256)
     assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 40000, 2048) == 0   # register-resident cluster kernel
     assert _lib.lib.pn2_furthest_point_sampling_workspace_bytes(8, 2048, 1024) == 0
     # PN2_FPS_THROUGHPUT (1): the bucketed kernel already from 32 768 points; PN2_FPS_LATENCY (0) = the plain query
