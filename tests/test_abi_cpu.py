@@ -252,3 +252,40 @@ def test_reencoder_training_path_matches_oracle_and_differentiates():
         torch.testing.assert_close(d["auxiliary_task_loc_gt"], want_prior, rtol=1e-4, atol=1e-8)
         d["scene_feat"].square().mean().backward()
         assert tokens.grad is not None and pe[0].weight.grad is not None and pe[2].weight.grad.abs().sum() > 0
+
+
+def test_sampling_mode_switch_and_training_fallbacks_on_cpu():
+    """Host logic that needs no GPU: the sampling-mode context manager restores the previous mode (also on error), the
+    pipeline's rule of thumb, and the row-layout training helpers fall back to PyTorch ops for CPU tensors."""
+    import torch
+    from situation3d_b200 import fused, train_rows
+    from situation3d_b200.graphs import pick_sampling_mode
+    assert fused._SAMPLING_MODE[0] == 0
+    with fused.sampling_mode("throughput"):
+        assert fused._SAMPLING_MODE[0] == 1
+        with fused.sampling_mode("latency"):
+            assert fused._SAMPLING_MODE[0] == 0
+        assert fused._SAMPLING_MODE[0] == 1
+    assert fused._SAMPLING_MODE[0] == 0
+    with pytest.raises(KeyError):
+        with fused.sampling_mode("fastest"):
+            pass
+    with pytest.raises(ZeroDivisionError):
+        with fused.sampling_mode("throughput"):
+            1 / 0
+    assert fused._SAMPLING_MODE[0] == 0
+    assert pick_sampling_mode(8) == "latency" and pick_sampling_mode(127) == "latency" and pick_sampling_mode(128) == "throughput"
+    # SharedMLP on rows with CPU tensors: the hand-written BatchNorm kernels are refused, torch ops give the module's result
+    from situation3d_b200.pointnet2 import pytorch_utils as pt_utils
+    torch.manual_seed(0)
+    mlp = pt_utils.SharedMLP([7, 16, 8], bn=True).train()
+    x = torch.randn(2 * 5 * 4, 7)
+    assert not train_rows._fused_bn_relu_ok(mlp[0], x, 0)
+    assert not train_rows._group_rows_ok(torch.randn(2, 10, 4), torch.randn(2, 10, 3))
+    import copy
+    ref = copy.deepcopy(mlp)
+    got = train_rows.shared_mlp_rows(mlp, x, pool_ns=4)                                      # (10, 8)
+    want = ref(x.view(2, 5, 4, 7).permute(0, 3, 1, 2)).amax(dim=3).permute(0, 2, 1).reshape(10, 8)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    for (n1, b1), (_, b2) in zip(mlp.named_buffers(), ref.named_buffers()):
+        torch.testing.assert_close(b1.float(), b2.float(), rtol=1e-5, atol=1e-6, msg=n1)
