@@ -18,7 +18,7 @@
 //
 // The ReLU mask is recomputed from x (pre > 0 <=> x*a + b > 0): nothing but x is kept for the backward pass.
 // Statistics are accumulated per thread in fp32 over <= a few hundred rows, merged in double in shared memory and
-// written as one partial per CTA (no atomics: deterministic); a one-CTA finalize kernel adds the partials in a fixed
+// written as one partial per CTA (no atomics: deterministic); a small finalize kernel adds the partials in a fixed
 // order and forms mean / variance / running statistics (forward) or the parameter gradients and the coefficients of the
 // input gradient (backward) in double -- two launches per layer and direction, no host synchronisation.
 //
@@ -93,17 +93,20 @@ bn_stats_kernel(long long rows, int c, const float *__restrict__ x, double *__re
 
 constexpr int kFinThreads = 1024;
 
-// Sum of the partial slots for every channel, by all threads of a one-CTA finalize kernel: thread (lane, ch) adds the
-// slots lane, lane + L, ... (L = blockDim / c lanes, fixed order), lane 0 adds the L results.  Returns true on the
-// threads that hold a channel's totals (s1, s2).
+// Sum of the partial slots for the 32 channels of this CTA (finalize kernels: one CTA per 32 channels, so that no single
+// SM has to pull all (nparts x 2c) doubles through its L2 port -- one CTA for 256 channels took 15 us): thread
+// (lane, j) adds the slots lane, lane + 32, ... of channel 32*blockIdx.x + j in a fixed order, lane 0 adds the 32
+// results.  Returns true on the threads that hold a channel's totals (s1, s2).
+constexpr int kFinChannels = 32;
 __device__ __forceinline__ bool sum_partials(int c, int nparts, const double *__restrict__ partials, int &ch, double &s1,
                                              double &s2)
 {
     __shared__ double fin[2][kFinThreads];
-    const int L = max(1, (int)blockDim.x / c), lane = threadIdx.x / c;
-    ch = threadIdx.x % c;
+    constexpr int L = kFinThreads / kFinChannels;
+    const int lane = threadIdx.x / kFinChannels, j = threadIdx.x % kFinChannels;
+    ch = blockIdx.x * kFinChannels + j;
     double a1 = 0.0, a2 = 0.0;
-    if (lane < L) {
+    if (ch < c) {
         int p = lane;
         for (; p + 3 * L < nparts; p += 4 * L) {           // eight independent loads in flight (the slots sit in L2)
             double u[4], v[4];
@@ -123,13 +126,13 @@ __device__ __forceinline__ bool sum_partials(int c, int nparts, const double *__
     fin[0][threadIdx.x] = a1;
     fin[1][threadIdx.x] = a2;
     __syncthreads();
-    if (lane != 0) return false;
+    if (lane != 0 || ch >= c) return false;
     s1 = 0.0; s2 = 0.0;
-    for (int l = 0; l < L; ++l) { s1 += fin[0][l * c + ch]; s2 += fin[1][l * c + ch]; }
+    for (int l = 0; l < L; ++l) { s1 += fin[0][l * kFinChannels + j]; s2 += fin[1][l * kFinChannels + j]; }
     return true;
 }
 
-// Forward finalize (one CTA): batch mean / biased variance from the partials, a = gamma/sqrt(var+eps), b = beta - mean*a,
+// Forward finalize (one CTA per 32 channels): batch mean / biased variance from the partials, a = gamma/sqrt(var+eps), b = beta - mean*a,
 // stat = [mean | 1/sqrt(var+eps)] in double for the backward pass, and nn.BatchNorm2d's running-statistics update
 // (running_var takes the unbiased variance) when the buffers are given.
 __global__ void __launch_bounds__(kFinThreads)
@@ -155,7 +158,7 @@ bn_finalize_kernel(int c, int nparts, const double *__restrict__ partials, doubl
     }
 }
 
-// Backward finalize (one CTA): from [sum g | sum g*x] the parameter gradients and the coefficients of
+// Backward finalize (one CTA per 32 channels): from [sum g | sum g*x] the parameter gradients and the coefficients of
 // dx = gamma*s*(g - mean(g) - x_hat*mean(g*x_hat)) = k1*g + k2 + k3*x   (s = 1/sqrt(var+eps), x_hat = (x - mean)*s)
 __global__ void __launch_bounds__(kFinThreads)
 bn_bwd_finalize_kernel(int c, int nparts, const double *__restrict__ partials, double rows, const double *__restrict__ stat,
@@ -394,8 +397,8 @@ extern "C" int pn2_rows_bn_finalize(int c, int nparts, const double *partials, l
                                     const float *bias, float momentum, float *running_mean, float *running_var, float *a,
                                     float *b, double *stat, pn2_stream_t stream)
 {
-    if (c < 1 || c > kFinThreads || nparts < 1 || rows < 1 || !partials || !weight || !bias || !a || !b || !stat) return PN2_ERR_INVALID_ARGUMENT;
-    bn_finalize_kernel<<<1, kFinThreads, 0, as_stream(stream)>>>(c, nparts, partials, (double)rows, eps, weight, bias, momentum,
+    if (c < 1 || nparts < 1 || rows < 1 || !partials || !weight || !bias || !a || !b || !stat) return PN2_ERR_INVALID_ARGUMENT;
+    bn_finalize_kernel<<<(c + kFinChannels - 1) / kFinChannels, kFinThreads, 0, as_stream(stream)>>>(c, nparts, partials, (double)rows, eps, weight, bias, momentum,
                                                           running_mean, running_var, a, b, stat);
     PN2_LAUNCH_CHECK("rows_bn_finalize");
     return PN2_OK;
@@ -405,9 +408,9 @@ extern "C" int pn2_rows_bn_bwd_finalize(int c, int nparts, const double *partial
                                         const float *weight, float *k1, float *k2, float *k3, float *dgamma, float *dbeta,
                                         pn2_stream_t stream)
 {
-    if (c < 1 || c > kFinThreads || nparts < 1 || rows < 1 || !partials || !stat || !weight || !k1 || !k2 || !k3 || !dgamma || !dbeta)
+    if (c < 1 || nparts < 1 || rows < 1 || !partials || !stat || !weight || !k1 || !k2 || !k3 || !dgamma || !dbeta)
         return PN2_ERR_INVALID_ARGUMENT;
-    bn_bwd_finalize_kernel<<<1, kFinThreads, 0, as_stream(stream)>>>(c, nparts, partials, (double)rows, stat, weight, k1, k2, k3,
+    bn_bwd_finalize_kernel<<<(c + kFinChannels - 1) / kFinChannels, kFinThreads, 0, as_stream(stream)>>>(c, nparts, partials, (double)rows, stat, weight, k1, k2, k3,
                                                               dgamma, dbeta);
     PN2_LAUNCH_CHECK("rows_bn_bwd_finalize");
     return PN2_OK;
