@@ -36,6 +36,24 @@ def rows_supported(mlp):
     return True
 
 
+class _OnDevice:
+    """``with _OnDevice(dev):`` -- torch.cuda.device(dev) only when ``dev`` is not already current (the training step is
+    host-bound: ~350 launches per step, and the guard's two cudaSetDevice calls per launch add up)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 class _BnReluRows(torch.autograd.Function):
     """Training-mode BatchNorm (batch statistics, biased variance) + ReLU [+ max over each group of ``pool_ns`` consecutive
     rows] on a (rows, C) matrix: csrc/train_rows.cu.  ``running_mean`` / ``running_var`` (or None) are updated in place
@@ -45,26 +63,29 @@ class _BnReluRows(torch.autograd.Function):
     def forward(ctx, x, weight, bias, eps, pool_ns, momentum, running_mean, running_var):
         R, C = x.shape
         dev = x.device
+        st = stream_ptr()
         partials = torch.empty(lib.pn2_rows_bn_partials_bytes(R, C) // 8, dtype=torch.float64, device=dev)
         coef = torch.empty((2, C), dtype=torch.float32, device=dev)          # a | b
         stat = torch.empty((2, C), dtype=torch.float64, device=dev)          # mean | invstd
         nparts = ctypes.c_int(0)
         w, b_ = weight.detach().contiguous(), bias.detach().contiguous()
-        with torch.cuda.device(dev):
-            check(lib.pn2_rows_bn_stats(R, C, ptr(x), ptr(partials), ctypes.byref(nparts), stream_ptr()), "rows_bn_stats")
+        pa = ctypes.c_void_p(coef.data_ptr())
+        pb = ctypes.c_void_p(coef.data_ptr() + 4 * C)
+        with _OnDevice(dev):
+            check(lib.pn2_rows_bn_stats(R, C, ptr(x), ptr(partials), ctypes.byref(nparts), st), "rows_bn_stats")
             check(lib.pn2_rows_bn_finalize(C, nparts.value, ptr(partials), R, float(eps), ptr(w), ptr(b_), float(momentum),
-                                           ptr(running_mean), ptr(running_var), ptr(coef[0]), ptr(coef[1]), ptr(stat),
-                                           stream_ptr()), "rows_bn_finalize")
+                                           ptr(running_mean), ptr(running_var), pa, pb, ptr(stat),
+                                           st), "rows_bn_finalize")
             if pool_ns:
                 groups = R // pool_ns
                 out = torch.empty((groups, C), dtype=torch.float32, device=dev)
                 arg = torch.empty((groups, C), dtype=torch.uint8, device=dev)
-                check(lib.pn2_rows_bn_relu_pool(groups, pool_ns, C, ptr(x), ptr(coef[0]), ptr(coef[1]), ptr(out), ptr(arg),
-                                                stream_ptr()), "rows_bn_relu_pool")
+                check(lib.pn2_rows_bn_relu_pool(groups, pool_ns, C, ptr(x), pa, pb, ptr(out), ptr(arg),
+                                                st), "rows_bn_relu_pool")
             else:
                 out = torch.empty_like(x)
                 arg = None
-                check(lib.pn2_rows_bn_relu_apply(R, C, ptr(x), ptr(coef[0]), ptr(coef[1]), ptr(out), stream_ptr()),
+                check(lib.pn2_rows_bn_relu_apply(R, C, ptr(x), pa, pb, ptr(out), st),
                       "rows_bn_relu_apply")
         ctx.pool_ns = pool_ns
         ctx.save_for_backward(x, w, coef, stat, arg)
@@ -75,28 +96,30 @@ class _BnReluRows(torch.autograd.Function):
         x, w, coef, stat, arg = ctx.saved_tensors
         R, C = x.shape
         dev = x.device
+        st = stream_ptr()
         dout = dout.contiguous()
         partials = torch.empty(lib.pn2_rows_bn_partials_bytes(R, C) // 8, dtype=torch.float64, device=dev)
         k = torch.empty((5, C), dtype=torch.float32, device=dev)             # k1 | k2 | k3 | dgamma | dbeta
         dx = torch.empty_like(x)
         nparts = ctypes.c_int(0)
         ns = ctx.pool_ns
-        a, b = ptr(coef[0]), ptr(coef[1])
-        with torch.cuda.device(dev):
+        a, b = ctypes.c_void_p(coef.data_ptr()), ctypes.c_void_p(coef.data_ptr() + 4 * C)
+        kp = [ctypes.c_void_p(k.data_ptr() + 4 * C * i) for i in range(5)]
+        with _OnDevice(dev):
             if ns:
                 check(lib.pn2_rows_bn_relu_pool_bwd_reduce(R // ns, ns, C, ptr(dout), ptr(x), ptr(arg), a, b, ptr(partials),
-                                                           ctypes.byref(nparts), stream_ptr()), "rows_bn_relu_pool_bwd_reduce")
+                                                           ctypes.byref(nparts), st), "rows_bn_relu_pool_bwd_reduce")
             else:
                 check(lib.pn2_rows_bn_relu_bwd_reduce(R, C, ptr(dout), ptr(x), a, b, ptr(partials), ctypes.byref(nparts),
-                                                      stream_ptr()), "rows_bn_relu_bwd_reduce")
-            check(lib.pn2_rows_bn_bwd_finalize(C, nparts.value, ptr(partials), R, ptr(stat), ptr(w), ptr(k[0]), ptr(k[1]),
-                                               ptr(k[2]), ptr(k[3]), ptr(k[4]), stream_ptr()), "rows_bn_bwd_finalize")
+                                                      st), "rows_bn_relu_bwd_reduce")
+            check(lib.pn2_rows_bn_bwd_finalize(C, nparts.value, ptr(partials), R, ptr(stat), ptr(w), kp[0], kp[1],
+                                               kp[2], kp[3], kp[4], st), "rows_bn_bwd_finalize")
             if ns:
-                check(lib.pn2_rows_bn_relu_pool_bwd_apply(R // ns, ns, C, ptr(dout), ptr(x), ptr(arg), a, b, ptr(k[0]), ptr(k[1]),
-                                                          ptr(k[2]), ptr(dx), stream_ptr()), "rows_bn_relu_pool_bwd_apply")
+                check(lib.pn2_rows_bn_relu_pool_bwd_apply(R // ns, ns, C, ptr(dout), ptr(x), ptr(arg), a, b, kp[0], kp[1],
+                                                          kp[2], ptr(dx), st), "rows_bn_relu_pool_bwd_apply")
             else:
-                check(lib.pn2_rows_bn_relu_bwd_apply(R, C, ptr(dout), ptr(x), a, b, ptr(k[0]), ptr(k[1]), ptr(k[2]), ptr(dx),
-                                                     stream_ptr()), "rows_bn_relu_bwd_apply")
+                check(lib.pn2_rows_bn_relu_bwd_apply(R, C, ptr(dout), ptr(x), a, b, kp[0], kp[1], kp[2], ptr(dx),
+                                                     st), "rows_bn_relu_bwd_apply")
         return dx, k[3], k[4], None, None, None, None, None
 
 
@@ -110,9 +133,10 @@ class _GroupRows(torch.autograd.Function):
         C = rows.shape[2]
         npoint, ns = idx.shape[1], idx.shape[2]
         out = torch.empty((B * npoint * ns, C + 3), dtype=torch.float32, device=rows.device)
-        with torch.cuda.device(rows.device):
+        st = stream_ptr()
+        with _OnDevice(rows.device):
             check(lib.pn2_group_rows(B, N, npoint, ns, C, ld, ptr(idx), ptr(xyz), ptr(new_xyz), ptr(rows), float(radius),
-                                     int(bool(normalize)), ptr(out), stream_ptr()), "group_rows")
+                                     int(bool(normalize)), ptr(out), st), "group_rows")
         ctx.save_for_backward(idx)
         ctx.shape = (B, N, C)
         return out
